@@ -1,0 +1,62 @@
+"""In-tree build of libhsrb.so (nvcc, sm_100a only).  ``python -m hsr_env_b200.build [--force]``.
+
+The shared library is built next to the sources (``hsr_env_b200/csrc/libhsrb.so``) so that it travels to the
+GPU box with the repository snapshot; it is git-ignored.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "libhsrb.so"
+TUS = ["hsrb_api.cu", "hsrb_step_g4.cu", "hsrb_step_g8.cu", "hsrb_step_g16.cu", "hsrb_step_g32.cu"]
+HEADERS = ["hsr_core.h", "hsr_model.h", "hsrb_kernels.cuh", "../../include/hsrb.h"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    hdrs = [CSRC / h for h in HEADERS]
+    objs = []
+    jobs = []
+    for tu in TUS:
+        src = CSRC / tu
+        obj = CSRC / (src.stem + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        (CSRC / (src.stem + ".ptxas.log")).write_text(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stderr}")
+        return src.name, r.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            for name, log in ex.map(compile_one, jobs):
+                if verbose:
+                    print(f"--- {name}\n{log}")
+    if force or jobs or _stale(LIB, objs):
+        cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

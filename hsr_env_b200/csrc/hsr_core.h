@@ -1,0 +1,1367 @@
+// One physics substep (mj_step semantics) for one environment, executed
+// cooperatively by a group of G lanes.  The same source is compiled
+//   * by nvcc for sm_100a with T=float and G in {4,8,16,32} lanes of a warp per environment
+//     (hsrb_kernels.cu; the per-environment workspace WS<T> lives in shared memory for all substeps), and
+//   * by g++ with G=1 (oracle/cpu_port.cpp, T=double) as the CPU baseline / host-side cross-check.
+//
+// Replaces the body of sim.step() at /root/reference/hsr/env.py:123 (MuJoCo's mj_step, not in the tree).
+//
+// Execution model inside a group: values held in registers are computed redundantly and are bit-identical on
+// all lanes (butterfly reductions preserve this); every workspace address is written by exactly one lane in a
+// phase and phases are separated by g.sync().
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "hsr_model.h"
+
+#if defined(__CUDACC__)
+#define HSR_HD __host__ __device__ __forceinline__
+#define HSR_HDN __host__ __device__ __noinline__
+#else
+#define HSR_HD inline
+#define HSR_HDN inline
+#endif
+
+namespace hsr {
+
+using std::cos; using std::fabs; using std::fmax; using std::fmin; using std::pow; using std::sin; using std::sqrt;
+
+template <typename T> struct Lim;
+template <> struct Lim<float> {
+  HSR_HD static float eps() { return FLT_EPSILON; }
+  HSR_HD static float minval() { return 1e-15f; }
+};
+template <> struct Lim<double> {
+  HSR_HD static double eps() { return DBL_EPSILON; }
+  HSR_HD static double minval() { return 1e-15; }
+};
+
+enum { FLAG_CON_OVERFLOW = 1, FLAG_BAD_NUM = 2, FLAG_CHOL = 4 };
+enum { WI_NCON = 0, WI_NEFC = 1, WI_NLIMIT = 2, WI_FLAGS = 3, WI_ITER = 4, WI_NARROW = 5, WI_LSEVAL = 6, WI_KFLOP = 7,
+       WI_SUMCON = 8, WI_SUMEFC = 9, WI_NPFLOP = 10, WI_COUNT = 12 };
+#define HSR_LSQ 10
+
+// ------------------------------------------------------------------------------------------------ groups
+struct HostGrp {
+  static constexpr int G = 1;
+  int lane = 0;
+  template <typename T> HSR_HD T sum(T x) const { return x; }
+  template <typename T> HSR_HD void argmax(T&, int&) const {}
+  HSR_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  HSR_HD void sync() const {}
+};
+
+#if defined(__CUDACC__)
+template <int G_>
+struct DevGrp {
+  static constexpr int G = G_;
+  int lane;       // lane inside the group
+  unsigned mask;  // member mask of the group inside its warp
+  int shift;      // first warp lane of the group
+  __device__ __forceinline__ DevGrp() {
+    int wl = threadIdx.x & 31;
+    lane = wl % G_;
+    shift = wl - lane;
+    mask = (G_ == 32) ? 0xffffffffu : (((1u << G_) - 1u) << shift);
+  }
+  template <typename T> __device__ __forceinline__ T sum(T x) const {
+#pragma unroll
+    for (int o = G_ / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
+    return x;
+  }
+  template <typename T> __device__ __forceinline__ void argmax(T& v, int& i) const {
+#pragma unroll
+    for (int o = G_ / 2; o > 0; o >>= 1) {
+      T ov = __shfl_xor_sync(mask, v, o);
+      int oi = __shfl_xor_sync(mask, i, o);
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+  }
+  __device__ __forceinline__ unsigned ballot(bool p) const {
+    unsigned b = __ballot_sync(mask, p) >> shift;
+    return (G_ == 32) ? b : (b & ((1u << G_) - 1u));
+  }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------------ vec3
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> HSR_HD V3<T> mk(T x, T y, T z) { V3<T> v; v.x = x; v.y = y; v.z = z; return v; }
+template <typename T> HSR_HD V3<T> ld3(const T* p) { return mk<T>(p[0], p[1], p[2]); }
+template <typename T> HSR_HD void st3(T* p, V3<T> v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+template <typename T> HSR_HD V3<T> operator+(V3<T> a, V3<T> b) { return mk<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> HSR_HD V3<T> operator-(V3<T> a, V3<T> b) { return mk<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> HSR_HD V3<T> operator-(V3<T> a) { return mk<T>(-a.x, -a.y, -a.z); }
+template <typename T> HSR_HD V3<T> operator*(V3<T> a, T s) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> HSR_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> HSR_HD V3<T> cross(V3<T> a, V3<T> b) {
+  return mk<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <typename T> HSR_HD T norm(V3<T> a) { return sqrt(dot(a, a)); }
+template <typename T> HSR_HD V3<T> normalized(V3<T> a) { return a * (T(1) / norm(a)); }
+template <typename T> HSR_HD T comp(V3<T> a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// 3x3 row-major helpers
+template <typename T> HSR_HD V3<T> mcol(const T* R, int k) { return mk<T>(R[k], R[3 + k], R[6 + k]); }
+template <typename T> HSR_HD V3<T> mulv(const T* R, V3<T> v) {
+  return mk<T>(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z,
+               R[6] * v.x + R[7] * v.y + R[8] * v.z);
+}
+template <typename T> HSR_HD V3<T> multv(const T* R, V3<T> v) {  // R^T v
+  return mk<T>(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z,
+               R[2] * v.x + R[5] * v.y + R[8] * v.z);
+}
+template <typename T> HSR_HD void mulm(const T* A, const T* B, T* C) {  // C = A B
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+template <typename T> HSR_HD void quat2mat(const T* q, T* R) {
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+template <typename T> HSR_HD void quatmul(const T* a, const T* b, T* r) {
+  T r0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T r1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T r2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T r3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3;
+}
+template <typename T> HSR_HD void quatnormalize(T* q) {
+  T n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < Lim<T>::minval()) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  T inv = T(1) / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+template <typename T>
+struct WS {
+  T *qpos, *qvel, *warm, *ctrl, *mocap;
+  T *xpos, *xquat, *xmat, *xipos, *anchor, *axis;
+  T *cdof, *cinert, *binert;
+  T *M, *L, *H;
+  T *qfrc_smooth, *qacc_smooth, *qacc, *Ma, *grad, *search, *Mv, *tmpv;
+  T *gpos, *gaabb;
+  T *con_dist, *con_pos, *con_frame, *con_mu;
+  T *J, *W, *D, *aref, *jar, *jv, *force;
+  T *lsq;
+  int *con_pair, *con_adr, *con_zone;
+  int* wi;
+};
+
+// Carve the workspace out of `base` (nullptr: just return the size in bytes).
+template <typename T>
+HSR_HD size_t ws_carve(const ModelT<T>& m, WS<T>* w, unsigned char* base) {
+  size_t off = 0;
+  WS<T> dummy;
+  if (!w) w = &dummy;
+#define CARVE(field, type, n) { w->field = (type*)(base + off); off += sizeof(type) * (size_t)(n); }
+  int nv = m.nv, nb = m.nbody, nc = m.ncon_max, ne = m.nefc_max;
+  CARVE(qpos, T, m.nq) CARVE(qvel, T, nv) CARVE(warm, T, nv) CARVE(ctrl, T, m.nu > 0 ? m.nu : 1) CARVE(mocap, T, 3)
+  CARVE(xpos, T, nb * 3) CARVE(xquat, T, nb * 4) CARVE(xmat, T, nb * 9) CARVE(xipos, T, nb * 3)
+  CARVE(anchor, T, m.njnt * 3) CARVE(axis, T, m.njnt * 3)
+  CARVE(cdof, T, nv * 6) CARVE(cinert, T, nb * 10) CARVE(binert, T, nb * 10)
+  CARVE(M, T, nv * nv) CARVE(L, T, nv * nv) CARVE(H, T, nv * nv)
+  CARVE(qfrc_smooth, T, nv) CARVE(qacc_smooth, T, nv) CARVE(qacc, T, nv) CARVE(Ma, T, nv) CARVE(grad, T, nv)
+  CARVE(search, T, nv) CARVE(Mv, T, nv) CARVE(tmpv, T, nv)
+  CARVE(gpos, T, m.ngeom * 3) CARVE(gaabb, T, m.ngeom * 3)
+  CARVE(con_dist, T, nc) CARVE(con_pos, T, nc * 3) CARVE(con_frame, T, nc * 9) CARVE(con_mu, T, nc)
+  CARVE(J, T, ne * nv) CARVE(W, T, ne * nv) CARVE(D, T, ne) CARVE(aref, T, ne) CARVE(jar, T, ne) CARVE(jv, T, ne)
+  CARVE(force, T, ne) CARVE(lsq, T, nc * HSR_LSQ)
+  CARVE(con_pair, int, nc) CARVE(con_adr, int, nc) CARVE(con_zone, int, nc) CARVE(wi, int, WI_COUNT)
+#undef CARVE
+  off += (16 - off % 16) % 16;
+  return off;
+}
+
+// ------------------------------------------------------------------------------------------------ B.1 kinematics
+// 10-number spatial inertia about the world origin: Ixx Iyy Izz Ixy Ixz Iyz  m*cx m*cy m*cz  m
+template <typename T> HSR_HD void inert_mul(const T* I, const T* v, T* f) {  // f = I * v,  v=[ang;lin], f=[torque;force]
+  V3<T> w = ld3(v), vo = ld3(v + 3), mc = ld3(I + 6);
+  V3<T> fl = vo * I[9] + cross(w, mc);
+  V3<T> fa = mk<T>(I[0] * w.x + I[3] * w.y + I[4] * w.z, I[3] * w.x + I[1] * w.y + I[5] * w.z,
+                   I[4] * w.x + I[5] * w.y + I[2] * w.z) + cross(mc, vo);
+  st3(f, fa); st3(f + 3, fl);
+}
+
+template <typename T>
+HSR_HD void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
+  // world
+  for (int k = 0; k < 3; k++) { w.xpos[k] = 0; w.xipos[k] = 0; }
+  for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? T(1) : T(0);
+  w.xquat[0] = 1; w.xquat[1] = w.xquat[2] = w.xquat[3] = 0;
+  for (int k = 0; k < 10; k++) { w.binert[k] = 0; }
+  for (int b = 1; b < m.nbody; b++) {
+    int p = m.body_parent[b];
+    int j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
+    T pos[3], quat[4], R[9];
+    if (nj == 1 && m.jnt_type[j0] == JNT_FREE) {
+      int a = m.jnt_qposadr[j0];
+      quatnormalize(w.qpos + a + 3);
+      for (int k = 0; k < 3; k++) pos[k] = w.qpos[a + k];
+      for (int k = 0; k < 4; k++) quat[k] = w.qpos[a + 3 + k];
+      for (int k = 0; k < 3; k++) w.anchor[3 * j0 + k] = pos[k];
+      quat2mat(quat, R);
+    } else {
+      V3<T> pp = ld3(w.xpos + 3 * p) + mulv(w.xmat + 9 * p, ld3(m.body_pos + 3 * b));
+      st3(pos, pp);
+      quatmul(w.xquat + 4 * p, m.body_quat + 4 * b, quat);
+      quat2mat(quat, R);
+      for (int j = j0; j < j0 + nj; j++) {
+        V3<T> anc = ld3(pos) + mulv(R, ld3(m.jnt_pos + 3 * j));
+        V3<T> ax = mulv(R, ld3(m.jnt_axis + 3 * j));
+        st3(w.anchor + 3 * j, anc); st3(w.axis + 3 * j, ax);
+        T q = w.qpos[m.jnt_qposadr[j]] - m.qpos0[m.jnt_qposadr[j]];
+        if (m.jnt_type[j] == JNT_SLIDE) {
+          st3(pos, ld3(pos) + ax * q);
+        } else {
+          T h = q * T(0.5), s = sin(h);
+          T dq[4] = {cos(h), s * m.jnt_axis[3 * j], s * m.jnt_axis[3 * j + 1], s * m.jnt_axis[3 * j + 2]};
+          quatmul(quat, dq, quat);
+          quat2mat(quat, R);
+          st3(pos, anc - mulv(R, ld3(m.jnt_pos + 3 * j)));
+        }
+      }
+      quatnormalize(quat);
+      quat2mat(quat, R);
+    }
+    for (int k = 0; k < 3; k++) w.xpos[3 * b + k] = pos[k];
+    for (int k = 0; k < 4; k++) w.xquat[4 * b + k] = quat[k];
+    for (int k = 0; k < 9; k++) w.xmat[9 * b + k] = R[k];
+    V3<T> c = ld3(pos) + mulv(R, ld3(m.body_ipos + 3 * b));
+    st3(w.xipos + 3 * b, c);
+    // spatial inertia about the world origin
+    const T* ib = m.body_inertia + 6 * b;
+    T Ib[9] = {ib[0], ib[3], ib[4], ib[3], ib[1], ib[5], ib[4], ib[5], ib[2]};
+    T tmp[9], Iw[9], Rt[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+    mulm(R, Ib, tmp); mulm(tmp, Rt, Iw);
+    T mass = m.body_mass[b];
+    T cc = dot(c, c);
+    T* I = w.binert + 10 * b;
+    I[0] = Iw[0] + mass * (cc - c.x * c.x); I[1] = Iw[4] + mass * (cc - c.y * c.y); I[2] = Iw[8] + mass * (cc - c.z * c.z);
+    I[3] = Iw[1] - mass * c.x * c.y; I[4] = Iw[2] - mass * c.x * c.z; I[5] = Iw[5] - mass * c.y * c.z;
+    I[6] = mass * c.x; I[7] = mass * c.y; I[8] = mass * c.z; I[9] = mass;
+  }
+  // composite inertias (leaf -> root)
+  for (int k = 0; k < 10 * m.nbody; k++) w.cinert[k] = w.binert[k];
+  for (int b = m.nbody - 1; b > 0; b--) {
+    int p = m.body_parent[b];
+    if (p > 0) for (int k = 0; k < 10; k++) w.cinert[10 * p + k] += w.cinert[10 * b + k];
+  }
+}
+
+// B.2 (part): motion axes about the world origin, [ang; lin]; geom centres + world AABB half extents
+template <typename T, typename Grp>
+HSR_HD void cdof_geoms(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  for (int j = g.lane; j < m.njnt; j += Grp::G) {
+    int a = m.jnt_dofadr[j], b = m.jnt_body[j], t = m.jnt_type[j];
+    if (t == JNT_FREE) {
+      V3<T> xp = ld3(w.xpos + 3 * b);
+      for (int k = 0; k < 3; k++) {
+        T* c = w.cdof + 6 * (a + k);
+        for (int i = 0; i < 6; i++) c[i] = (i == 3 + k) ? T(1) : T(0);
+        V3<T> ax = mcol(w.xmat + 9 * b, k);
+        T* cr = w.cdof + 6 * (a + 3 + k);
+        st3(cr, ax); st3(cr + 3, cross(xp, ax));
+      }
+    } else if (t == JNT_SLIDE) {
+      T* c = w.cdof + 6 * a;
+      c[0] = c[1] = c[2] = 0; st3(c + 3, ld3(w.axis + 3 * j));
+    } else {
+      T* c = w.cdof + 6 * a;
+      V3<T> ax = ld3(w.axis + 3 * j);
+      st3(c, ax); st3(c + 3, cross(ld3(w.anchor + 3 * j), ax));
+    }
+  }
+  for (int gi = g.lane; gi < m.ngeom; gi += Grp::G) {
+    int b = m.geom_body[gi];
+    const T* R = w.xmat + 9 * b;
+    st3(w.gpos + 3 * gi, ld3(w.xpos + 3 * b) + mulv(R, ld3(m.geom_pos + 3 * gi)));
+    T Rg[9];
+    mulm(R, m.geom_mat + 9 * gi, Rg);
+    const T* h = m.geom_aabb + 3 * gi;
+    for (int i = 0; i < 3; i++)
+      w.gaabb[3 * gi + i] = fabs(Rg[3 * i]) * h[0] + fabs(Rg[3 * i + 1]) * h[1] + fabs(Rg[3 * i + 2]) * h[2];
+  }
+}
+
+// B.2: dense joint-space inertia by the composite-rigid-body method; one dof row per lane
+template <typename T, typename Grp>
+HSR_HD void mass_matrix(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  int nv = m.nv;
+  for (int i = g.lane; i < nv; i += Grp::G) {
+    T f[6];
+    inert_mul(w.cinert + 10 * m.dof_body[i], w.cdof + 6 * i, f);
+    for (int j = 0; j < nv; j++) if (j > i || !((m.body_dofmask[m.dof_body[i]] >> j) & 1u)) w.M[i * nv + j] = 0;
+    int j = i;
+    while (j >= 0) {
+      const T* c = w.cdof + 6 * j;
+      T v = c[0] * f[0] + c[1] * f[1] + c[2] * f[2] + c[3] * f[3] + c[4] * f[4] + c[5] * f[5];
+      w.M[i * nv + j] = v;
+      j = m.dof_parent[j];
+    }
+  }
+  g.sync();
+  // mirror to the upper triangle (each lane mirrors its own rows' transposes)
+  for (int i = g.lane; i < nv; i += Grp::G)
+    for (int j = i + 1; j < nv; j++) w.M[i * nv + j] = w.M[j * nv + i];
+}
+
+// dense Cholesky A = L L^T (lower, in place) and solves; serial (lane 0)
+template <typename T> HSR_HD bool chol_factor(T* A, int n) {
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    T d = A[k * n + k];
+    for (int j = 0; j < k; j++) d -= A[k * n + j] * A[k * n + j];
+    if (!(d > Lim<T>::minval())) { d = Lim<T>::minval(); ok = false; }
+    d = sqrt(d);
+    A[k * n + k] = d;
+    T inv = T(1) / d;
+    for (int i = k + 1; i < n; i++) {
+      T s = A[i * n + k];
+      for (int j = 0; j < k; j++) s -= A[i * n + j] * A[k * n + j];
+      A[i * n + k] = s * inv;
+    }
+  }
+  return ok;
+}
+template <typename T> HSR_HD void chol_solve(const T* L, int n, T* x) {
+  for (int i = 0; i < n; i++) {
+    T s = x[i];
+    for (int j = 0; j < i; j++) s -= L[i * n + j] * x[j];
+    x[i] = s / L[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    T s = x[i];
+    for (int j = i + 1; j < n; j++) s -= L[j * n + i] * x[j];
+    x[i] = s / L[i * n + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ B.6 smooth dynamics
+template <typename T> HSR_HD void cross_motion(const T* v, const T* s, T* r) {
+  V3<T> va = ld3(v), vl = ld3(v + 3), sa = ld3(s), sl = ld3(s + 3);
+  st3(r, cross(va, sa)); st3(r + 3, cross(va, sl) + cross(vl, sa));
+}
+template <typename T> HSR_HD void cross_force(const T* v, const T* f, T* r) {
+  V3<T> va = ld3(v), vl = ld3(v + 3), fa = ld3(f), fl = ld3(f + 3);
+  st3(r, cross(va, fa) + cross(vl, fl)); st3(r + 3, cross(va, fl));
+}
+
+// lane 0: RNE bias, passive, actuation -> qfrc_smooth; factor M -> L; qacc_smooth
+template <typename T>
+HSR_HD void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
+  int nv = m.nv;
+  T cvel[HSRB_MAXBODY][6], cacc[HSRB_MAXBODY][6], cfrc[HSRB_MAXBODY][6];
+  for (int k = 0; k < 6; k++) { cvel[0][k] = 0; cacc[0][k] = 0; cfrc[0][k] = 0; }
+  cacc[0][3] = -m.gravity[0]; cacc[0][4] = -m.gravity[1]; cacc[0][5] = -m.gravity[2];
+  for (int b = 1; b < m.nbody; b++) {
+    int p = m.body_parent[b];
+    T v[6], a[6], t[6];
+    for (int k = 0; k < 6; k++) { v[k] = cvel[p][k]; a[k] = cacc[p][k]; }
+    for (int j = m.body_jntadr[b]; j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
+      int d0 = m.jnt_dofadr[j];
+      if (m.jnt_type[j] == JNT_FREE) {
+        for (int k = 0; k < 3; k++) for (int i = 0; i < 6; i++) v[i] += w.cdof[6 * (d0 + k) + i] * w.qvel[d0 + k];
+        T vt[6];
+        for (int i = 0; i < 6; i++) vt[i] = v[i];
+        for (int k = 3; k < 6; k++) {
+          cross_motion(vt, w.cdof + 6 * (d0 + k), t);
+          for (int i = 0; i < 6; i++) { a[i] += t[i] * w.qvel[d0 + k]; v[i] += w.cdof[6 * (d0 + k) + i] * w.qvel[d0 + k]; }
+        }
+      } else {
+        cross_motion(v, w.cdof + 6 * d0, t);
+        for (int i = 0; i < 6; i++) { a[i] += t[i] * w.qvel[d0]; v[i] += w.cdof[6 * d0 + i] * w.qvel[d0]; }
+      }
+    }
+    T Ia[6], Iv[6];
+    inert_mul(w.binert + 10 * b, a, Ia);
+    inert_mul(w.binert + 10 * b, v, Iv);
+    cross_force(v, Iv, t);
+    for (int k = 0; k < 6; k++) { cvel[b][k] = v[k]; cacc[b][k] = a[k]; cfrc[b][k] = Ia[k] + t[k]; }
+  }
+  for (int b = m.nbody - 1; b > 0; b--) {
+    int p = m.body_parent[b];
+    if (p > 0) for (int k = 0; k < 6; k++) cfrc[p][k] += cfrc[b][k];
+  }
+  for (int i = 0; i < nv; i++) {
+    const T* c = w.cdof + 6 * i;
+    const T* f = cfrc[m.dof_body[i]];
+    T bias = c[0] * f[0] + c[1] * f[1] + c[2] * f[2] + c[3] * f[3] + c[4] * f[4] + c[5] * f[5];
+    w.qfrc_smooth[i] = -m.dof_damping[i] * w.qvel[i] - bias;
+  }
+  for (int a = 0; a < m.nu; a++) {
+    T c = w.ctrl[a];
+    if (m.act_ctrllimited[a]) c = fmin(fmax(c, m.act_ctrlrange[2 * a]), m.act_ctrlrange[2 * a + 1]);
+    T f = m.act_kp[a] * c - m.act_kp[a] * m.act_gear[a] * w.qpos[m.act_qposadr[a]];
+    if (m.act_forcelimited[a]) f = fmin(fmax(f, m.act_forcerange[2 * a]), m.act_forcerange[2 * a + 1]);
+    w.qfrc_smooth[m.act_dof[a]] += m.act_gear[a] * f;
+  }
+  for (int k = 0; k < nv * nv; k++) w.L[k] = w.M[k];
+  if (!chol_factor(w.L, nv)) w.wi[WI_FLAGS] |= FLAG_CHOL;
+  for (int i = 0; i < nv; i++) w.qacc_smooth[i] = w.qfrc_smooth[i];
+  chol_solve(w.L, nv, w.qacc_smooth);
+}
+
+// ------------------------------------------------------------------------------------------------ B.3 collision
+template <typename T> struct Geom {
+  int type; const T* size; const T* verts; int nvert; V3<T> pos; T mat[9];
+};
+
+template <typename T>
+HSR_HD void load_geom(const ModelT<T>& m, const WS<T>& w, int gi, Geom<T>& ge) {
+  ge.type = m.geom_type[gi]; ge.size = m.geom_size + 3 * gi;
+  ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
+  ge.pos = ld3(w.gpos + 3 * gi);
+  mulm(w.xmat + 9 * m.geom_body[gi], m.geom_mat + 9 * gi, ge.mat);
+}
+
+// support point in world direction d (mjccd_support, margin 0); hull vertices are scanned by all lanes
+template <typename T, typename Grp>
+HSR_HD V3<T> support(const Geom<T>& ge, V3<T> d, const Grp& g) {
+  V3<T> dl = multv(ge.mat, d), res;
+  if (ge.type == GEOM_BOX) {
+    res = mk<T>(dl.x >= 0 ? ge.size[0] : -ge.size[0], dl.y >= 0 ? ge.size[1] : -ge.size[1],
+                dl.z >= 0 ? ge.size[2] : -ge.size[2]);
+  } else if (ge.type == GEOM_CYLINDER) {
+    T n = sqrt(dl.x * dl.x + dl.y * dl.y);
+    res = mk<T>(0, 0, dl.z >= 0 ? ge.size[1] : -ge.size[1]);
+    if (n > Lim<T>::minval()) { res.x = dl.x / n * ge.size[0]; res.y = dl.y / n * ge.size[0]; }
+  } else {
+    T best = -FLT_MAX; int bi = 0x7fffffff;
+    for (int i = g.lane; i < ge.nvert; i += Grp::G) {
+      T v = ge.verts[3 * i] * dl.x + ge.verts[3 * i + 1] * dl.y + ge.verts[3 * i + 2] * dl.z;
+      if (v > best) { best = v; bi = i; }
+    }
+    g.argmax(best, bi);
+    res = ld3(ge.verts + 3 * bi);
+  }
+  return ge.pos + mulv(ge.mat, res);
+}
+
+template <typename T> HSR_HD void make_frame(V3<T> n, T* fr) {
+  n = normalized(n);
+  V3<T> t = (n.y > T(-0.5) && n.y < T(0.5)) ? mk<T>(0, 1, 0) : mk<T>(0, 0, 1);
+  t = t - n * dot(n, t);
+  t = normalized(t);
+  st3(fr, n); st3(fr + 3, t); st3(fr + 6, cross(n, t));
+}
+
+template <typename T, typename Grp>
+HSR_HD void add_contact(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, T dist, V3<T> pos,
+                        V3<T> n) {
+  int dim = m.pair_condim[pair];
+  if (ncon >= m.ncon_max || nrow + dim > m.nefc_max) {
+    if (g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CON_OVERFLOW;
+    return;
+  }
+  if (g.lane == 0) {
+    w.con_pair[ncon] = pair; w.con_dist[ncon] = dist; st3(w.con_pos + 3 * ncon, pos);
+    make_frame(n, w.con_frame + 9 * ncon);
+    w.con_adr[ncon] = nrow;
+  }
+  ncon++; nrow += dim;
+}
+
+template <typename T> struct Sup { V3<T> v, v1, v2; };
+
+template <typename T> HSR_HD bool is_zero(T x) { return fabs(x) < Lim<T>::eps(); }
+template <typename T> HSR_HD bool ccd_eq(T a, T b) {
+  T ab = fabs(a - b);
+  if (ab < Lim<T>::eps()) return true;
+  a = fabs(a); b = fabs(b);
+  return ab < Lim<T>::eps() * (b > a ? b : a);
+}
+
+// squared distance from the origin to triangle (a,b,c) with the closest point q
+template <typename T> HSR_HD T origin_tri_dist2(V3<T> a, V3<T> b, V3<T> c, V3<T>& q) {
+  V3<T> ab = b - a, ac = c - a, ap = -a;
+  T d1 = dot(ab, ap), d2 = dot(ac, ap);
+  if (d1 <= 0 && d2 <= 0) { q = a; return dot(q, q); }
+  V3<T> bp = -b;
+  T d3 = dot(ab, bp), d4 = dot(ac, bp);
+  if (d3 >= 0 && d4 <= d3) { q = b; return dot(q, q); }
+  T vc = d1 * d4 - d3 * d2;
+  V3<T> cp = -c;
+  T d5 = dot(ab, cp), d6 = dot(ac, cp);
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { q = a + ab * (d1 / (d1 - d3)); return dot(q, q); }
+  if (d6 >= 0 && d5 <= d6) { q = c; return dot(q, q); }
+  T vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { q = a + ac * (d2 / (d2 - d6)); return dot(q, q); }
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { q = b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6))); return dot(q, q); }
+  T den = T(1) / (va + vb + vc);
+  q = a + ab * (vb * den) + ac * (vc * den);
+  return dot(q, q);
+}
+
+// Minkowski Portal Refinement penetration query (libccd ccdMPRPenetration as used by mjc_Convex).
+template <typename T, typename Grp>
+HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, T tol, int max_iter, const Grp& g, T& depth,
+                             V3<T>& pdir, V3<T>& ppos) {
+  auto sup = [&](V3<T> d) { Sup<T> s; s.v1 = support(g1, d, g); s.v2 = support(g2, -d, g); s.v = s.v1 - s.v2; return s; };
+  auto reach_tol = [&](const Sup<T>& v1, const Sup<T>& v2, const Sup<T>& v3, const Sup<T>& v4, V3<T> d) {
+    T dv4 = dot(v4.v, d);
+    T d1 = dv4 - dot(v1.v, d), d2 = dv4 - dot(v2.v, d), d3 = dv4 - dot(v3.v, d);
+    T mn = fmin(d1, fmin(d2, d3));
+    return ccd_eq(mn, tol) || mn < tol;
+  };
+  auto expand = [&](const Sup<T>& v0, Sup<T>& v1, Sup<T>& v2, Sup<T>& v3, const Sup<T>& v4) {
+    V3<T> v4v0 = cross(v4.v, v0.v);
+    if (dot(v1.v, v4v0) > 0) {
+      if (dot(v2.v, v4v0) > 0) v1 = v4; else v3 = v4;
+    } else {
+      if (dot(v3.v, v4v0) > 0) v2 = v4; else v1 = v4;
+    }
+  };
+  const T eps = Lim<T>::eps();
+  Sup<T> v0, v1, v2, v3, v4;
+  v0.v1 = g1.pos; v0.v2 = g2.pos; v0.v = v0.v1 - v0.v2;
+  if (fabs(v0.v.x) < eps && fabs(v0.v.y) < eps && fabs(v0.v.z) < eps) v0.v.x += eps * 10;
+  V3<T> d = normalized(-v0.v);
+  v1 = sup(d);
+  T dt = dot(v1.v, d);
+  if (is_zero(dt) || dt < 0) return false;
+  d = cross(v0.v, v1.v);
+  if (is_zero(dot(d, d))) {
+    if (fabs(v1.v.x) < eps && fabs(v1.v.y) < eps && fabs(v1.v.z) < eps) return false;
+    depth = norm(v1.v); pdir = v1.v * (T(1) / depth); ppos = (v1.v1 + v1.v2) * T(0.5);
+    return true;
+  }
+  d = normalized(d);
+  v2 = sup(d);
+  dt = dot(v2.v, d);
+  if (is_zero(dt) || dt < 0) return false;
+  d = normalized(cross(v1.v - v0.v, v2.v - v0.v));
+  if (dot(d, v0.v) > 0) { Sup<T> t = v1; v1 = v2; v2 = t; d = -d; }
+  for (int guard = 0; guard < 64; guard++) {
+    v3 = sup(d);
+    dt = dot(v3.v, d);
+    if (is_zero(dt) || dt < 0) return false;
+    bool cont = false;
+    dt = dot(cross(v1.v, v3.v), v0.v);
+    if (dt < 0 && !is_zero(dt)) { v2 = v3; cont = true; }
+    if (!cont) {
+      dt = dot(cross(v3.v, v2.v), v0.v);
+      if (dt < 0 && !is_zero(dt)) { v1 = v3; cont = true; }
+    }
+    if (!cont) break;
+    d = normalized(cross(v1.v - v0.v, v2.v - v0.v));
+  }
+  // refine the portal until it encapsulates the origin
+  for (int guard = 0; guard < 256; guard++) {
+    d = normalized(cross(v2.v - v1.v, v3.v - v1.v));
+    dt = dot(d, v1.v);
+    if (is_zero(dt) || dt > 0) break;
+    v4 = sup(d);
+    dt = dot(v4.v, d);
+    if (!(is_zero(dt) || dt > 0) || reach_tol(v1, v2, v3, v4, d)) return false;
+    expand(v0, v1, v2, v3, v4);
+  }
+  // find penetration
+  int it = 0;
+  while (true) {
+    d = normalized(cross(v2.v - v1.v, v3.v - v1.v));
+    v4 = sup(d);
+    if (reach_tol(v1, v2, v3, v4, d) || it > max_iter) {
+      V3<T> q;
+      T d2 = origin_tri_dist2(v1.v, v2.v, v3.v, q);
+      depth = sqrt(d2);
+      if (is_zero(depth)) return false;
+      pdir = q * (T(1) / norm(q));
+      T b0 = dot(cross(v1.v, v2.v), v3.v), b1 = dot(cross(v3.v, v2.v), v0.v), b2 = dot(cross(v0.v, v1.v), v3.v),
+        b3 = dot(cross(v2.v, v1.v), v0.v);
+      T s = b0 + b1 + b2 + b3;
+      if (is_zero(s) || s < 0) {
+        b0 = 0; b1 = dot(cross(v2.v, v3.v), d); b2 = dot(cross(v3.v, v1.v), d); b3 = dot(cross(v1.v, v2.v), d);
+        s = b1 + b2 + b3;
+      }
+      T inv = T(1) / s;
+      V3<T> p1 = (v0.v1 * b0 + v1.v1 * b1 + v2.v1 * b2 + v3.v1 * b3) * inv;
+      V3<T> p2 = (v0.v2 * b0 + v1.v2 * b1 + v2.v2 * b2 + v3.v2 * b3) * inv;
+      ppos = (p1 + p2) * T(0.5);
+      return true;
+    }
+    expand(v0, v1, v2, v3, v4);
+    it++;
+  }
+}
+
+// Box-box manifold (SAT over 15 axes, face clipping with <=8 points, or one edge-edge contact); see oracle box_box.
+template <typename T, typename Grp>
+HSR_HDN void box_box(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, const Geom<T>& A,
+                     const Geom<T>& B) {
+  const T* R1 = A.mat; const T* R2 = B.mat; const T* s1 = A.size; const T* s2 = B.size;
+  V3<T> p1 = A.pos, p2 = B.pos, d = p2 - p1;
+  T C[9], Q[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    C[3 * i + j] = dot(mcol(R1, i), mcol(R2, j)); Q[3 * i + j] = fabs(C[3 * i + j]) + T(1e-10);
+  }
+  V3<T> dl1 = multv(R1, d), dl2 = multv(R2, d);
+  T best = -FLT_MAX; int code = -1; V3<T> n = mk<T>(0, 0, 1);
+  for (int i = 0; i < 3; i++) {
+    T dd = comp(dl1, i);
+    T sep = fabs(dd) - (s1[i] + Q[3 * i] * s2[0] + Q[3 * i + 1] * s2[1] + Q[3 * i + 2] * s2[2]);
+    if (sep > 0) return;
+    if (sep > best) { best = sep; code = i; n = mcol(R1, i) * (dd >= 0 ? T(1) : T(-1)); }
+  }
+  for (int i = 0; i < 3; i++) {
+    T dd = comp(dl2, i);
+    T sep = fabs(dd) - (s2[i] + Q[i] * s1[0] + Q[3 + i] * s1[1] + Q[6 + i] * s1[2]);
+    if (sep > 0) return;
+    if (sep > best) { best = sep; code = 3 + i; n = mcol(R2, i) * (dd >= 0 ? T(1) : T(-1)); }
+  }
+  T ebest = -FLT_MAX; int ecode = -1; V3<T> en = n;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    V3<T> ax = cross(mcol(R1, i), mcol(R2, j));
+    T ln = norm(ax);
+    if (ln < T(1e-4)) continue;
+    ax = ax * (T(1) / ln);
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    T ra = s1[i1] * fabs(dot(mcol(R1, i1), ax)) + s1[i2] * fabs(dot(mcol(R1, i2), ax));
+    T rb = s2[j1] * fabs(dot(mcol(R2, j1), ax)) + s2[j2] * fabs(dot(mcol(R2, j2), ax));
+    T dd = dot(d, ax);
+    T sep = fabs(dd) - (ra + rb);
+    if (sep > 0) return;
+    if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; en = ax * (dd >= 0 ? T(1) : T(-1)); }
+  }
+  if (ecode >= 0 && T(1.05) * ebest > best) { best = ebest; code = ecode; n = en; }
+  if (code >= 6) {
+    int i = (code - 6) / 3, j = (code - 6) % 3;
+    V3<T> pa = p1, pb = p2;
+    for (int k = 0; k < 3; k++) {
+      if (k != i) pa = pa + mcol(R1, k) * (s1[k] * (dot(mcol(R1, k), n) > 0 ? T(1) : T(-1)));
+      if (k != j) pb = pb - mcol(R2, k) * (s2[k] * (dot(mcol(R2, k), n) > 0 ? T(1) : T(-1)));
+    }
+    V3<T> ua = mcol(R1, i), ub = mcol(R2, j), ww = pa - pb;
+    T a_ = dot(ua, ua), b_ = dot(ua, ub), c_ = dot(ub, ub), d_ = dot(ua, ww), e_ = dot(ub, ww);
+    T den = a_ * c_ - b_ * b_;
+    T ta = (b_ * e_ - c_ * d_) / den, tb = (a_ * e_ - b_ * d_) / den;
+    ta = fmin(fmax(ta, -s1[i]), s1[i]); tb = fmin(fmax(tb, -s2[j]), s2[j]);
+    V3<T> ca = pa + ua * ta, cb = pb + ub * tb;
+    add_contact(m, w, g, ncon, nrow, pair, best, (ca + cb) * T(0.5), n);
+    return;
+  }
+  const T *Rr, *sr, *Ri, *si; V3<T> pr, pi, nr; int ax;
+  if (code < 3) { pr = p1; Rr = R1; sr = s1; pi = p2; Ri = R2; si = s2; nr = n; ax = code; }
+  else { pr = p2; Rr = R2; sr = s2; pi = p1; Ri = R1; si = s1; nr = -n; ax = code - 3; }
+  V3<T> dots = multv(Ri, nr);
+  int k = 0;
+  if (fabs(dots.y) > fabs(comp(dots, k))) k = 1;
+  if (fabs(dots.z) > fabs(comp(dots, k))) k = 2;
+  T sgn = comp(dots, k) > 0 ? T(-1) : T(1);
+  V3<T> fc = pi + mcol(Ri, k) * (si[k] * sgn);
+  int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+  V3<T> u = mcol(Ri, k1) * si[k1], v = mcol(Ri, k2) * si[k2];
+  V3<T> poly[16], tmp[16];
+  int np = 4;
+  poly[0] = fc + u + v; poly[1] = fc - u + v; poly[2] = fc - u - v; poly[3] = fc + u - v;
+  int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+  for (int side = 0; side < 4; side++) {
+    int axis_id = side < 2 ? a1 : a2;
+    T sg = (side & 1) ? T(-1) : T(1);
+    V3<T> pn = mcol(Rr, axis_id) * sg;
+    T off = dot(pn, pr) + sr[axis_id];
+    int nn = 0;
+    for (int q = 0; q < np; q++) {
+      V3<T> Aq = poly[q], Bq = poly[(q + 1) % np];
+      T da = dot(pn, Aq) - off, db = dot(pn, Bq) - off;
+      if (da <= 0) tmp[nn++] = Aq;
+      if ((da < 0 && db > 0) || (db < 0 && da > 0)) tmp[nn++] = Aq + (Bq - Aq) * (da / (da - db));
+    }
+    np = nn;
+    for (int q = 0; q < np; q++) poly[q] = tmp[q];
+    if (np == 0) return;
+  }
+  T face_off = dot(nr, pr) + sr[ax];
+  int cnt = 0;
+  for (int q = 0; q < np && cnt < 8; q++) {
+    T dep = face_off - dot(nr, poly[q]);
+    if (dep < 0) continue;
+    add_contact(m, w, g, ncon, nrow, pair, -dep, poly[q] + nr * (dep * T(0.5)), n);
+    cnt++;
+  }
+}
+
+// Candidate pairs -> bounding sphere + conservative world-AABB cull -> narrowphase.  Returns #contacts;
+// nrow is advanced by the constraint rows the contacts will occupy.
+template <typename T, typename Grp>
+HSR_HD int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
+  int ncon = 0;
+  int narrow = 0, npflop = 0;
+  for (int base = 0; base < m.npair; base += Grp::G) {
+    int k = base + g.lane;
+    bool hit = false;
+    if (k < m.npair) {
+      int a = m.pair_geom1[k], b = m.pair_geom2[k];
+      V3<T> dp = ld3(w.gpos + 3 * b) - ld3(w.gpos + 3 * a);
+      if (m.geom_type[a] == GEOM_PLANE) {
+        const T* R = w.xmat + 9 * m.geom_body[a];  // plane geoms sit on the world body with identity geom_mat rows
+        T Rg[9];
+        mulm(R, m.geom_mat + 9 * a, Rg);
+        hit = dot(dp, mcol(Rg, 2)) <= m.geom_rbound[b];
+      } else {
+        T rr = m.geom_rbound[a] + m.geom_rbound[b];
+        hit = dot(dp, dp) <= rr * rr;
+        const T* ha = w.gaabb + 3 * a; const T* hb = w.gaabb + 3 * b;
+        hit = hit && fabs(dp.x) <= ha[0] + hb[0] && fabs(dp.y) <= ha[1] + hb[1] && fabs(dp.z) <= ha[2] + hb[2];
+      }
+    }
+    unsigned bits = g.ballot(hit);
+    while (bits) {
+      int l = 0;
+      while (!((bits >> l) & 1u)) l++;
+      bits &= bits - 1;
+      int pk = base + l;
+      narrow++;
+      Geom<T> A, B;
+      load_geom(m, w, m.pair_geom1[pk], A);
+      load_geom(m, w, m.pair_geom2[pk], B);
+      int func = m.pair_func[pk];
+      npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
+      if (func == NP_PLANE_BOX) {
+        V3<T> n = mcol(A.mat, 2);
+        T dist0 = dot(B.pos - A.pos, n);
+        int cnt = 0;
+        for (int i = 0; i < 8 && cnt < 4; i++) {
+          V3<T> s = mk<T>((i & 1) ? B.size[0] : -B.size[0], (i & 2) ? B.size[1] : -B.size[1], (i & 4) ? B.size[2] : -B.size[2]);
+          V3<T> vec = mulv(B.mat, s);
+          T ld = dot(n, vec);
+          if (dist0 + ld > 0 || ld > 0) continue;
+          T dist = dist0 + ld;
+          add_contact(m, w, g, ncon, nrow, pk, dist, B.pos + vec - n * (dist * T(0.5)), n);
+          cnt++;
+        }
+      } else if (func == NP_PLANE_CONVEX) {
+        V3<T> n = mcol(A.mat, 2);
+        V3<T> p = support(B, -n, g);
+        T dist = dot(p - A.pos, n);
+        if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * T(0.5)), n);
+      } else if (func == NP_BOX_BOX) {
+        box_box(m, w, g, ncon, nrow, pk, A, B);
+      } else {
+        T depth; V3<T> dir, pos;
+        if (mpr_penetration(A, B, m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+          add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
+      }
+    }
+  }
+  if (g.lane == 0) { w.wi[WI_NARROW] += narrow; w.wi[WI_NPFLOP] = npflop; }
+  return ncon;
+}
+
+// ------------------------------------------------------------------------------------------------ B.4 / B.5
+template <typename T> HSR_HD T impedance(const T* solimp, T pos) {
+  const T MINIMP = T(1e-4), MAXIMP = T(0.9999);
+  T d0 = fmin(fmax(solimp[0], MINIMP), MAXIMP), dmax = fmin(fmax(solimp[1], MINIMP), MAXIMP);
+  T width = fmax(Lim<T>::minval(), solimp[2]), mid = fmin(fmax(solimp[3], MINIMP), MAXIMP), power = fmax(T(1), solimp[4]);
+  if (d0 == dmax || width <= Lim<T>::minval()) return T(0.5) * (d0 + dmax);
+  T x = fabs(pos) / width;
+  if (x >= 1) return dmax;
+  if (x == 0) return d0;
+  T y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = (T(1) / pow(mid, power - 1)) * pow(x, power);
+  else y = T(1) - (T(1) / pow(1 - mid, power - 1)) * pow(1 - x, power);
+  return d0 + y * (dmax - d0);
+}
+
+// reference acceleration + regulariser of one scalar row
+template <typename T>
+HSR_HD void row_params(const ModelT<T>& m, const T* solref, const T* solimp, T pos, T vel, T diag, bool friction_row,
+                       T& R, T& aref) {
+  T tc = fmax(solref[0], 2 * m.timestep), dr = solref[1];
+  T dmax = fmin(fmax(solimp[1], T(1e-4)), T(0.9999));
+  T imp = impedance(solimp, pos);
+  R = fmax(Lim<T>::minval(), (1 - imp) / imp * diag);
+  T k = friction_row ? T(0) : T(1) / (dmax * dmax * tc * tc * dr * dr);
+  T b = T(2) / (dmax * tc);
+  aref = -b * vel - k * imp * pos;
+}
+
+// rows: active joint limits (joint order) then contacts (elliptic, dim rows each)
+template <typename T, typename Grp>
+HSR_HD void make_constraint(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon) {
+  int nv = m.nv;
+  // limit rows (recomputed by every lane; lane 0 writes)
+  if (g.lane == 0) {
+    int r = 0;
+    for (int j = 0; j < m.njnt; j++) {
+      if (!m.jnt_limited[j] || m.jnt_type[j] == JNT_FREE) continue;
+      T q = w.qpos[m.jnt_qposadr[j]];
+      int dof = m.jnt_dofadr[j];
+      for (int side = 0; side < 2; side++) {
+        T dist = side == 0 ? q - m.jnt_range[2 * j] : m.jnt_range[2 * j + 1] - q;
+        if (dist < 0) {
+          T sg = side == 0 ? T(1) : T(-1);
+          for (int d = 0; d < nv; d++) w.J[r * nv + d] = (d == dof) ? sg : T(0);
+          T R, aref;
+          row_params(m, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, sg * w.qvel[dof], m.dof_invweight0[dof], false, R, aref);
+          w.D[r] = T(1) / R; w.aref[r] = aref;
+          r++;
+        }
+      }
+    }
+  }
+  // contact Jacobians: dof columns across lanes
+  for (int c = 0; c < ncon; c++) {
+    int pk = w.con_pair[c];
+    int dim = m.pair_condim[pk], r0 = w.con_adr[c];
+    uint32_t m1 = m.body_dofmask[m.geom_body[m.pair_geom1[pk]]], m2 = m.body_dofmask[m.geom_body[m.pair_geom2[pk]]];
+    V3<T> p = ld3(w.con_pos + 3 * c);
+    const T* fr = w.con_frame + 9 * c;
+    for (int d = g.lane; d < nv; d += Grp::G) {
+      T sg = T((m2 >> d) & 1u) - T((m1 >> d) & 1u);
+      const T* cd = w.cdof + 6 * d;
+      V3<T> jr = ld3(cd) * sg;
+      V3<T> jp = (ld3(cd + 3) + cross(ld3(cd), p)) * sg;
+      for (int r = 0; r < dim; r++)
+        w.J[(r0 + r) * nv + d] = r < 3 ? dot(ld3(fr + 3 * r), jp) : dot(ld3(fr + 3 * (r - 3)), jr);
+    }
+  }
+  g.sync();
+  // per-contact row parameters: one contact per lane
+  for (int c = g.lane; c < ncon; c += Grp::G) {
+    int pk = w.con_pair[c];
+    int dim = m.pair_condim[pk], r0 = w.con_adr[c];
+    const T* fri = m.pair_friction + 5 * pk;
+    T diag = m.geom_invweight[m.pair_geom1[pk]] + m.geom_invweight[m.pair_geom2[pk]];
+    T R0 = 0;
+    for (int r = 0; r < dim; r++) {
+      T vel = 0;
+      for (int d = 0; d < nv; d++) vel += w.J[(r0 + r) * nv + d] * w.qvel[d];
+      T R, aref;
+      row_params(m, m.pair_solref + 2 * pk, m.pair_solimp + 5 * pk, r == 0 ? w.con_dist[c] : T(0), vel, diag, r > 0, R, aref);
+      if (r == 0) R0 = R;
+      else if (r == 1) R = R0 / m.impratio;
+      else R = (R0 / m.impratio) * fri[0] * fri[0] / (fri[r - 1] * fri[r - 1]);
+      w.D[r0 + r] = T(1) / R; w.aref[r0 + r] = aref;
+    }
+    w.con_mu[c] = dim > 1 ? fri[0] * sqrt((R0 / m.impratio) / R0) : fri[0];
+  }
+  (void)nlimit;
+}
+
+// ------------------------------------------------------------------------------------------------ B.7 solver
+// zone of an elliptic contact given jar rows x: 0 top (no force), 1 bottom (quadratic), 2 middle (cone)
+template <typename T>
+HSR_HD int cone_zone(const T* x, int dim, T mu, const T* fri, T& N, T& Tn) {
+  N = x[0] * mu;
+  T tt = 0;
+  for (int j = 1; j < dim; j++) { T u = x[j] * fri[j - 1]; tt += u * u; }
+  Tn = sqrt(tt);
+  if (N >= mu * Tn || (Tn <= 0 && N >= 0)) return 0;
+  if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) return 1;
+  return 2;
+}
+
+// constraint cost of the current w.jar (rows across lanes / one contact per lane); optionally force + W rows
+template <typename T, typename Grp>
+HSR_HD T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, bool full) {
+  int nv = m.nv;
+  T cost = 0;
+  for (int i = g.lane; i < nlimit; i += Grp::G) {
+    T x = w.jar[i];
+    bool act = x < 0;
+    if (act) cost += T(0.5) * w.D[i] * x * x;
+    if (full) {
+      w.force[i] = act ? -w.D[i] * x : T(0);
+      T s = act ? w.D[i] : T(0);
+      for (int d = 0; d < nv; d++) w.W[i * nv + d] = s * w.J[i * nv + d];
+    }
+  }
+  for (int c = g.lane; c < ncon; c += Grp::G) {
+    int pk = w.con_pair[c];
+    int dim = m.pair_condim[pk], r0 = w.con_adr[c];
+    const T* fri = m.pair_friction + 5 * pk;
+    T mu = w.con_mu[c];
+    const T* x = w.jar + r0;
+    T N, Tn;
+    int zone;
+    if (dim == 1) { zone = x[0] < 0 ? 1 : 0; N = x[0]; Tn = 0; }
+    else zone = cone_zone(x, dim, mu, fri, N, Tn);
+    if (full) w.con_zone[c] = zone;
+    if (zone == 0) {
+      if (full) for (int r = 0; r < dim; r++) { w.force[r0 + r] = 0; for (int d = 0; d < nv; d++) w.W[(r0 + r) * nv + d] = 0; }
+    } else if (zone == 1) {
+      for (int r = 0; r < dim; r++) {
+        T D = w.D[r0 + r];
+        cost += T(0.5) * D * x[r] * x[r];
+        if (full) { w.force[r0 + r] = -D * x[r]; for (int d = 0; d < nv; d++) w.W[(r0 + r) * nv + d] = D * w.J[(r0 + r) * nv + d]; }
+      }
+    } else {
+      T Dm = w.D[r0] / (mu * mu * (1 + mu * mu));
+      T NT = N - mu * Tn;
+      cost += T(0.5) * Dm * NT * NT;
+      if (full) {
+        T f0 = -Dm * NT * mu;
+        w.force[r0] = f0;
+        T U[6], scl[6];
+        scl[0] = mu; U[0] = N;
+        for (int j = 1; j < dim; j++) { scl[j] = fri[j - 1]; U[j] = x[j] * fri[j - 1]; w.force[r0 + j] = -f0 / Tn * U[j] * fri[j - 1]; }
+        // cone Hessian (in jar space) times the contact Jacobian rows -> W rows
+        T invT = T(1) / Tn;
+        T Hc[36];
+        for (int a = 0; a < dim; a++) for (int b = 0; b < dim; b++) {
+          T h;
+          if (a == 0 && b == 0) h = 1;
+          else if (a == 0) h = -mu * U[b] * invT;
+          else if (b == 0) h = -mu * U[a] * invT;
+          else {
+            T uu = U[a] * U[b] * invT * invT;
+            h = mu * mu * uu - mu * NT * ((a == b ? invT : T(0)) - uu * invT);
+          }
+          Hc[a * 6 + b] = Dm * scl[a] * h * scl[b];
+        }
+        for (int a = 0; a < dim; a++) for (int d = 0; d < nv; d++) {
+          T s = 0;
+          for (int b = 0; b < dim; b++) s += Hc[a * 6 + b] * w.J[(r0 + b) * nv + d];
+          w.W[(r0 + a) * nv + d] = s;
+        }
+      }
+    }
+  }
+  return g.sum(cost);
+}
+
+// jar = J x - aref (rows across lanes), Ma = M x (dofs across lanes); returns the Gauss term
+template <typename T, typename Grp>
+HSR_HD T residuals(const ModelT<T>& m, WS<T>& w, const Grp& g, const T* x, int nefc) {
+  int nv = m.nv;
+  for (int r = g.lane; r < nefc; r += Grp::G) {
+    T s = -w.aref[r];
+    for (int d = 0; d < nv; d++) s += w.J[r * nv + d] * x[d];
+    w.jar[r] = s;
+  }
+  T gauss = 0;
+  for (int i = g.lane; i < nv; i += Grp::G) {
+    T s = 0;
+    for (int d = 0; d < nv; d++) s += w.M[i * nv + d] * x[d];
+    w.Ma[i] = s;
+    gauss += T(0.5) * (s - w.qfrc_smooth[i]) * (x[i] - w.qacc_smooth[i]);
+  }
+  return g.sum(gauss);
+}
+
+template <typename T, typename Grp>
+HSR_HD void ls_eval(const ModelT<T>& m, const WS<T>& w, const Grp& g, int nlimit, int ncon, T alpha, T q1, T q2, T& c,
+                    T& d1, T& d2) {
+  T lc = 0, l1 = 0, l2 = 0;
+  for (int i = g.lane; i < nlimit; i += Grp::G) {
+    T x = w.jar[i] + alpha * w.jv[i];
+    if (x < 0) { T D = w.D[i]; lc += T(0.5) * D * x * x; l1 += D * x * w.jv[i]; l2 += D * w.jv[i] * w.jv[i]; }
+  }
+  for (int cc = g.lane; cc < ncon; cc += Grp::G) {
+    const T* q = w.lsq + HSR_LSQ * cc;
+    // q: U0 V0 UU UV VV  Q0 Q1 Q2  mu Dm
+    T mu = q[8];
+    T N = q[0] + alpha * q[1];
+    T tsq = q[2] + alpha * (2 * q[3] + alpha * q[4]);
+    T Tn = tsq > 0 ? sqrt(tsq) : T(0);
+    bool top = (N >= mu * Tn) || (Tn <= 0 && N >= 0);
+    bool bottom = (mu * N + Tn <= 0) || (Tn <= 0 && N < 0);
+    if (q[9] < 0) { top = !(N < 0); bottom = N < 0; }  // dim-1 contact: plain unilateral row
+    if (top) continue;
+    if (bottom) {
+      lc += q[5] + alpha * (q[6] + alpha * q[7]); l1 += q[6] + 2 * alpha * q[7]; l2 += 2 * q[7];
+      continue;
+    }
+    T Dm = q[9];
+    T NT = N - mu * Tn;
+    T N1 = q[1];
+    T T1 = (q[3] + alpha * q[4]) / Tn;
+    T T2 = q[4] / Tn - T1 * T1 / Tn;
+    lc += T(0.5) * Dm * NT * NT;
+    l1 += Dm * NT * (N1 - mu * T1);
+    l2 += Dm * ((N1 - mu * T1) * (N1 - mu * T1) - NT * mu * T2);
+  }
+  c = g.sum(lc) + alpha * q1 + alpha * alpha * q2;
+  d1 = g.sum(l1) + q1 + 2 * alpha * q2;
+  d2 = g.sum(l2) + 2 * q2;
+}
+
+// exact line search along w.search (safeguarded Newton on the 1-D derivative with bracketing)
+template <typename T, typename Grp>
+HSR_HD T linesearch(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, T gtol) {
+  int nv = m.nv;
+  T a1 = 0, a2 = 0;
+  for (int i = g.lane; i < nv; i += Grp::G) {
+    a1 += w.search[i] * (w.Ma[i] - w.qfrc_smooth[i]);
+    a2 += T(0.5) * w.search[i] * w.Mv[i];
+  }
+  T q1 = g.sum(a1), q2 = g.sum(a2);
+  for (int c = g.lane; c < ncon; c += Grp::G) {
+    int pk = w.con_pair[c];
+    int dim = m.pair_condim[pk], r0 = w.con_adr[c];
+    const T* fri = m.pair_friction + 5 * pk;
+    T mu = w.con_mu[c];
+    T* q = w.lsq + HSR_LSQ * c;
+    T uu = 0, uv = 0, vv = 0, Q0 = 0, Q1 = 0, Q2 = 0;
+    for (int r = 0; r < dim; r++) {
+      T x = w.jar[r0 + r], v = w.jv[r0 + r], D = w.D[r0 + r];
+      Q0 += T(0.5) * D * x * x; Q1 += D * x * v; Q2 += T(0.5) * D * v * v;
+      if (r > 0) { T u = x * fri[r - 1], s = v * fri[r - 1]; uu += u * u; uv += u * s; vv += s * s; }
+    }
+    if (dim == 1) { q[0] = w.jar[r0]; q[1] = w.jv[r0]; q[8] = 1; q[9] = -1; }
+    else { q[0] = w.jar[r0] * mu; q[1] = w.jv[r0] * mu; q[8] = mu; q[9] = w.D[r0] / (mu * mu * (1 + mu * mu)); }
+    q[2] = uu; q[3] = uv; q[4] = vv; q[5] = Q0; q[6] = Q1; q[7] = Q2;
+  }
+  g.sync();
+  T c0, d1, d2;
+  ls_eval(m, w, g, nlimit, ncon, T(0), q1, q2, c0, d1, d2);
+  int nev = 1;
+  T lo = 0, hi = -1, alpha = 0, bestc = c0, besta = 0;
+  for (int it = 0; it < m.ls_iterations; it++) {
+    if (fabs(d1) < gtol) break;
+    T step = d2 > Lim<T>::minval() ? -d1 / d2 : (d1 < 0 ? T(1) : T(-1));
+    T nxt = alpha + step;
+    if (hi >= 0 && !(lo < nxt && nxt < hi)) nxt = T(0.5) * (lo + hi);
+    if (nxt <= 0 && hi < 0) nxt = alpha * T(0.5);
+    if (nxt == alpha) break;
+    alpha = nxt;
+    T c;
+    ls_eval(m, w, g, nlimit, ncon, alpha, q1, q2, c, d1, d2);
+    nev++;
+    if (c < bestc) { bestc = c; besta = alpha; }
+    if (d1 < 0) lo = lo > alpha ? lo : alpha;
+    else hi = (hi < 0 || alpha < hi) ? alpha : hi;
+  }
+  if (g.lane == 0) w.wi[WI_LSEVAL] += nev;
+  return (bestc < c0 || fabs(d1) < gtol) ? besta : T(0);
+}
+
+// Newton solver on the primal convex cost; on exit w.qacc, w.force (and w.tmpv = J^T force) are final.
+template <typename T, typename Grp>
+HSR_HD void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc) {
+  int nv = m.nv;
+  if (nefc == 0) {
+    for (int i = g.lane; i < nv; i += Grp::G) { w.qacc[i] = w.qacc_smooth[i]; w.tmpv[i] = 0; }
+    g.sync();
+    return;
+  }
+  // warm start: lower cost of qacc_warmstart / qacc_smooth
+  T gw = residuals(m, w, g, w.warm, nefc);
+  g.sync();
+  T cw = constraint_update(m, w, g, nlimit, ncon, false) + gw;
+  g.sync();
+  T gs = residuals(m, w, g, w.qacc_smooth, nefc);
+  g.sync();
+  T cs = constraint_update(m, w, g, nlimit, ncon, false) + gs;
+  bool use_warm = cw <= cs;
+  for (int i = g.lane; i < nv; i += Grp::G) w.qacc[i] = use_warm ? w.warm[i] : w.qacc_smooth[i];
+  g.sync();
+  T gauss = use_warm ? residuals(m, w, g, w.qacc, nefc) : gs;
+  g.sync();
+  T cost = constraint_update(m, w, g, nlimit, ncon, true) + gauss;
+  g.sync();
+  T scale = T(1) / (m.meaninertia * T(nv > 1 ? nv : 1));
+  int it = 0;
+  while (true) {
+    // gradient (dofs across lanes) and Hessian H = M + J^T W (lower triangle entries across lanes)
+    T gn = 0;
+    for (int i = g.lane; i < nv; i += Grp::G) {
+      T s = w.Ma[i] - w.qfrc_smooth[i];
+      for (int r = 0; r < nefc; r++) s -= w.J[r * nv + i] * w.force[r];
+      w.grad[i] = s; gn += s * s;
+    }
+    gn = sqrt(g.sum(gn));
+    if (it > 0 && scale * gn < m.tolerance) break;
+    if (it >= m.iterations) break;
+    int ntri = nv * (nv + 1) / 2;
+    for (int e = g.lane; e < ntri; e += Grp::G) {
+      int a = 0, rem = e;
+      while (rem > a) { rem -= a + 1; a++; }
+      int b = rem;  // a >= b
+      T s = w.M[a * nv + b];
+      for (int r = 0; r < nefc; r++) s += w.J[r * nv + a] * w.W[r * nv + b];
+      w.H[a * nv + b] = s;
+    }
+    g.sync();
+    if (g.lane == 0) {
+      if (!chol_factor(w.H, nv)) w.wi[WI_FLAGS] |= FLAG_CHOL;
+      for (int i = 0; i < nv; i++) w.search[i] = -w.grad[i];
+      chol_solve(w.H, nv, w.search);
+    }
+    g.sync();
+    T sn = 0, dec = 0;
+    for (int i = g.lane; i < nv; i += Grp::G) { sn += w.search[i] * w.search[i]; dec -= w.grad[i] * w.search[i]; }
+    sn = sqrt(g.sum(sn));
+    dec = g.sum(dec);  // Newton decrement^2 = grad^T H^-1 grad
+    if (sn < Lim<T>::minval()) break;
+    for (int i = g.lane; i < nv; i += Grp::G) {
+      T s = 0;
+      for (int d = 0; d < nv; d++) s += w.M[i * nv + d] * w.search[d];
+      w.Mv[i] = s;
+    }
+    for (int r = g.lane; r < nefc; r += Grp::G) {
+      T s = 0;
+      for (int d = 0; d < nv; d++) s += w.J[r * nv + d] * w.search[d];
+      w.jv[r] = s;
+    }
+    g.sync();
+    T gtol = m.tolerance * m.ls_tolerance * sn / scale;
+    T alpha = linesearch(m, w, g, nlimit, ncon, gtol);
+    if (alpha == 0) break;
+    T gsum = 0;
+    for (int i = g.lane; i < nv; i += Grp::G) {
+      w.qacc[i] += alpha * w.search[i]; w.Ma[i] += alpha * w.Mv[i];
+      gsum += T(0.5) * (w.Ma[i] - w.qfrc_smooth[i]) * (w.qacc[i] - w.qacc_smooth[i]);
+    }
+    for (int r = g.lane; r < nefc; r += Grp::G) w.jar[r] += alpha * w.jv[r];
+    gsum = g.sum(gsum);
+    g.sync();
+    T old = cost;
+    cost = constraint_update(m, w, g, nlimit, ncon, true) + gsum;
+    g.sync();
+    it++;
+    // improvement of this step.  The reference tests old - cost; in fp32 that difference of two large numbers
+    // is rounding noise near convergence, so the quadratic-model prediction alpha (1 - alpha/2) grad^T H^-1 grad
+    // is used instead (equal to old - cost to second order, free of cancellation); the measured difference is
+    // kept only where the model does not apply (alpha >= 2).
+    T improvement = alpha < T(2) ? alpha * (T(1) - T(0.5) * alpha) * dec : old - cost;
+    if (scale * improvement < m.tolerance) break;
+  }
+  for (int i = g.lane; i < nv; i += Grp::G) {
+    T s = 0;
+    for (int r = 0; r < nefc; r++) s += w.J[r * nv + i] * w.force[r];
+    w.tmpv[i] = s;
+  }
+  if (g.lane == 0) w.wi[WI_ITER] += it;
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ B.8 Euler
+template <typename T>
+HSR_HD void euler_lane0(const ModelT<T>& m, WS<T>& w) {
+  int nv = m.nv;
+  T dt = m.timestep;
+  // qacc_int = (M + dt*diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
+  T* x = w.grad;  // scratch
+  if (m.any_damping) {
+    for (int k = 0; k < nv * nv; k++) w.H[k] = w.M[k];
+    for (int i = 0; i < nv; i++) { w.H[i * nv + i] += dt * m.dof_damping[i]; x[i] = w.qfrc_smooth[i] + w.tmpv[i]; }
+    if (!chol_factor(w.H, nv)) w.wi[WI_FLAGS] |= FLAG_CHOL;
+    chol_solve(w.H, nv, x);
+  } else {
+    for (int i = 0; i < nv; i++) x[i] = w.qacc[i];
+  }
+  bool bad = false;
+  for (int i = 0; i < nv; i++) {
+    w.warm[i] = w.qacc[i];
+    w.qvel[i] += dt * x[i];
+    if (!(fabs(w.qvel[i]) < T(1e6))) bad = true;
+  }
+  for (int j = 0; j < m.njnt; j++) {
+    int a = m.jnt_qposadr[j], v = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == JNT_FREE) {
+      for (int k = 0; k < 3; k++) w.qpos[a + k] += dt * w.qvel[v + k];
+      V3<T> om = ld3(w.qvel + v + 3);
+      T ang = norm(om);
+      quatnormalize(w.qpos + a + 3);
+      if (ang * dt > Lim<T>::minval()) {
+        T h = T(0.5) * ang * dt, s = sin(h) / ang;
+        T dq[4] = {cos(h), s * om.x, s * om.y, s * om.z};
+        quatmul(w.qpos + a + 3, dq, w.qpos + a + 3);
+      }
+      quatnormalize(w.qpos + a + 3);
+    } else {
+      w.qpos[a] += dt * w.qvel[v];
+    }
+  }
+  if (bad) w.wi[WI_FLAGS] |= FLAG_BAD_NUM;
+}
+
+// ------------------------------------------------------------------------------------------------ one substep
+// Algorithmic flop count of one substep: the stage formulas of SURVEY.md §8(d) evaluated with the substep's actual
+// contact / row / iteration / line-search counts (what bench.py's FP32 roofline numerator is made of).
+template <typename T>
+HSR_HD int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls, int npflop) {
+  int nv = m.nv, nb = m.nbody - 1, nfree = m.nblock;
+  bool articulated = false;  // any joint other than world-attached slides / free joints => M varies with qpos
+  for (int j = 0; j < m.njnt; j++)
+    if (m.jnt_type[j] == JNT_HINGE || m.body_parent[m.jnt_body[j]] > 0) articulated = true;
+  int f = 100 * nb + 60 * m.ngeom;                                   // FK + geom frames
+  if (articulated) f += 60 * nb + 20 * nv + nv * nv * nv / 3;          // CRB + factorisation
+  f += 9 * m.npair + npflop;                                           // broadphase + narrowphase
+  f += 150 * nc + 2 * ne * nv + 60 * nc;                               // contact frames, Jacobian, row parameters
+  f += 10 * nv + (articulated ? 150 * nb : 0);                         // passive + bias + actuation + qacc_smooth
+  if (ne > 0) {
+    f += 2 * (2 * ne * nv + 50 * nc + 4 * nv);                         // warm-start cost comparison
+    int its = it > 0 ? it : 1;
+    f += its * (50 * nc + ne * nv * nv + nv * nv * nv / 3 + 2 * ne * nv + 2 * nv * nv + 2 * ne * nv + 6 * ne);
+    f += ls * 70 * nc;                                                 // line-search evaluations
+  }
+  f += 6 * nv + 60 * nfree + 10;                                       // Euler, quaternion integration, goal test
+  return f;
+}
+
+// mj_forward up to and including the constraint solve (sim.forward(), /root/reference/hsr/env.py:176)
+template <typename T, typename Grp>
+HSR_HD void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  if (g.lane == 0) kinematics_lane0(m, w);
+  g.sync();
+  cdof_geoms(m, w, g);
+  g.sync();
+  mass_matrix(m, w, g);
+  g.sync();
+  if (g.lane == 0) smooth_lane0(m, w);
+  // active joint limits (uniform count)
+  int nlimit = 0;
+  for (int j = 0; j < m.njnt; j++) {
+    if (!m.jnt_limited[j] || m.jnt_type[j] == JNT_FREE) continue;
+    T q = w.qpos[m.jnt_qposadr[j]];
+    if (q - m.jnt_range[2 * j] < 0) nlimit++;
+    if (m.jnt_range[2 * j + 1] - q < 0) nlimit++;
+  }
+  int nrow = nlimit;
+  int ncon = collision(m, w, g, nrow);
+  g.sync();
+  make_constraint(m, w, g, nlimit, ncon);
+  int it0 = w.wi[WI_ITER], ls0 = w.wi[WI_LSEVAL];
+  g.sync();
+  if (g.lane == 0) { w.wi[WI_NCON] = ncon; w.wi[WI_NEFC] = nrow; w.wi[WI_NLIMIT] = nlimit; }
+  g.sync();
+  solve_newton(m, w, g, nlimit, ncon, nrow);
+  if (g.lane == 0) {
+    w.wi[WI_SUMCON] += ncon; w.wi[WI_SUMEFC] += nrow;
+    w.wi[WI_KFLOP] += algorithmic_flops(m, ncon, nrow, w.wi[WI_ITER] - it0, w.wi[WI_LSEVAL] - ls0, w.wi[WI_NPFLOP]);
+  }
+  g.sync();
+}
+
+// mj_step (sim.step(), /root/reference/hsr/env.py:123)
+template <typename T, typename Grp>
+HSR_HD void substep(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  forward(m, w, g);
+  if (g.lane == 0) euler_lane0(m, w);
+  g.sync();
+}
+
+// all(in_range(block_i, goal, geofence)) on the body positions of the last forward pass
+// (HSREnv.in_range / distance_between, /root/reference/hsr/env.py:137-147,231-232; strict <)
+template <typename T>
+HSR_HD bool goal_reached(const ModelT<T>& m, const EnvCfg<T>& cfg, const WS<T>& w) {
+  if (!cfg.has_goal || m.nblock == 0) return false;
+  bool all = true;
+  for (int k = 0; k < m.nblock; k++) {
+    const T* p = w.xpos + 3 * m.block_body[k];
+    T dx = p[0] - w.mocap[0], dy = p[1] - w.mocap[1], dz = p[2] - w.mocap[2];
+    T dist = sqrt(dx * dx + dy * dy + dz * dz);
+    all = all && (dist < cfg.geofence);
+  }
+  return all;
+}
+
+// HSREnv.step inner loop (/root/reference/hsr/env.py:118-131): up to nsub substeps, goal test after every
+// substep, freeze at the first success.  Returns the number of substeps executed.
+template <typename T, typename Grp>
+HSR_HD int env_action(const ModelT<T>& m, const EnvCfg<T>& cfg, WS<T>& w, const Grp& g, int nsub, bool& success) {
+  int taken = 0;
+  success = false;
+  for (int s = 0; s < nsub; s++) {
+    substep(m, w, g);
+    taken++;
+    if (goal_reached(m, cfg, w)) { success = true; break; }
+  }
+  return taken;
+}
+
+// Flat per-stage dump of the last forward pass (teacher-forced parity tests); layout mirrored in
+// hsr_env_b200/debug_layout.py.  Values are converted to double.
+template <typename T>
+HSR_HD size_t debug_size(const ModelT<T>& m) {
+  return 4 + (size_t)m.nbody * 3 + (size_t)m.nv * m.nv + 3 * (size_t)m.nv + (size_t)m.ncon_max * 14 +
+         (size_t)m.nefc_max * (m.nv + 3) + (size_t)m.nq + m.nv;
+}
+template <typename T>
+HSR_HD void debug_dump(const ModelT<T>& m, const WS<T>& w, double* o) {
+  size_t k = 0;
+  int nv = m.nv;
+  o[k++] = w.wi[WI_NCON]; o[k++] = w.wi[WI_NEFC]; o[k++] = w.wi[WI_NLIMIT]; o[k++] = w.wi[WI_ITER];
+  for (int i = 0; i < m.nbody * 3; i++) o[k++] = (double)w.xpos[i];
+  for (int i = 0; i < nv * nv; i++) o[k++] = (double)w.M[i];
+  for (int i = 0; i < nv; i++) o[k++] = (double)w.qfrc_smooth[i];
+  for (int i = 0; i < nv; i++) o[k++] = (double)w.qacc_smooth[i];
+  for (int i = 0; i < nv; i++) o[k++] = (double)w.qacc[i];
+  for (int c = 0; c < m.ncon_max; c++) {
+    bool on = c < w.wi[WI_NCON];
+    o[k++] = on ? (double)w.con_pair[c] : -1.0;
+    o[k++] = on ? (double)w.con_dist[c] : 0.0;
+    for (int i = 0; i < 3; i++) o[k++] = on ? (double)w.con_pos[3 * c + i] : 0.0;
+    for (int i = 0; i < 9; i++) o[k++] = on ? (double)w.con_frame[9 * c + i] : 0.0;
+  }
+  for (int r = 0; r < m.nefc_max; r++) {
+    bool on = r < w.wi[WI_NEFC];
+    for (int d = 0; d < nv; d++) o[k++] = on ? (double)w.J[r * nv + d] : 0.0;
+    o[k++] = on ? (double)w.D[r] : 0.0;
+    o[k++] = on ? (double)w.aref[r] : 0.0;
+    o[k++] = on ? (double)w.force[r] : 0.0;
+  }
+  for (int i = 0; i < m.nq; i++) o[k++] = (double)w.qpos[i];
+  for (int i = 0; i < nv; i++) o[k++] = (double)w.qvel[i];
+}
+
+// ------------------------------------------------------------------------------------------------ resets
+HSR_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform float32 in [lo, hi): lo + u*(hi-lo) with u = (x>>8)*2^-24, evaluated in fp32 without FMA contraction
+HSR_HD float uniform32(uint32_t x, float lo, float hi) {
+  float u = (float)(x >> 8) * (1.0f / 16777216.0f);
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(lo, __fmul_rn(u, __fsub_rn(hi, lo)));
+#else
+  volatile float span = hi - lo;
+  volatile float prod = u * span;
+  return lo + prod;
+#endif
+}
+
+// mj_resetData + HSREnv.reset_model (/root/reference/hsr/mujoco_env.py:83-85, hsr/env.py:158-177) for one env.
+// Philox4x32-10, key = (seed_lo, global env id), counter = (episode, draw block, seed_hi, 0).  lane 0 only.
+template <typename T>
+HSR_HD void reset_lane0(const ModelT<T>& m, const EnvCfg<T>& cfg, WS<T>& w, uint64_t seed, uint32_t env_id,
+                        uint32_t episode) {
+  for (int i = 0; i < m.nq; i++) w.qpos[i] = m.qpos0[i];
+  for (int i = 0; i < m.nv; i++) { w.qvel[i] = 0; w.warm[i] = 0; }
+  for (int i = 0; i < m.nu; i++) w.ctrl[i] = 0;
+  for (int k = 0; k < 3; k++) w.mocap[k] = m.mocap_pos0[k];
+  if (!cfg.has_goal) return;
+  uint32_t r[4];
+  uint32_t k0 = (uint32_t)seed, k1 = env_id, c2 = (uint32_t)(seed >> 32);
+  philox4x32_10(episode, 0, c2, 0, k0, k1, r);
+  for (int k = 0; k < 3; k++) w.mocap[k] = (T)uniform32(r[k], (float)cfg.goal_lo[k], (float)cfg.goal_hi[k]);
+  for (int b = 0; b < m.nblock && cfg.has_block; b++) {
+    int body = m.block_body[b];
+    int a = m.jnt_qposadr[m.body_jntadr[body]];
+    float s[4];
+    for (int tries = 0; tries < 16; tries++) {
+      philox4x32_10(episode, 1 + b * 16 + tries, c2, 0, k0, k1, r);
+      for (int k = 0; k < 4; k++) s[k] = uniform32(r[k], (float)cfg.block_lo[k], (float)cfg.block_hi[k]);
+      bool ok = true;
+      if (cfg.min_sep > 0)
+        for (int o = 0; o < b; o++) {
+          int ao = m.jnt_qposadr[m.body_jntadr[m.block_body[o]]];
+          T dx = (T)s[0] - w.qpos[ao], dy = (T)s[1] - w.qpos[ao + 1];
+          if (dx * dx + dy * dy < cfg.min_sep * cfg.min_sep) ok = false;
+        }
+      if (ok) break;
+    }
+    w.qpos[a] = (T)s[0]; w.qpos[a + 1] = (T)s[1];
+    w.qpos[a + 3] = w.qpos[a + 4] = w.qpos[a + 5] = w.qpos[a + 6] = 0;
+    w.qpos[a + 3 + cfg.qidx0] = (T)s[2]; w.qpos[a + 3 + cfg.qidx1] = (T)s[3];
+  }
+}
+
+}  // namespace hsr

@@ -1,0 +1,381 @@
+// libhsrb.so - C ABI of the batched physics backend (include/hsrb.h).
+//
+// Host side of the action kernel: owns the device copy of the model blob, the resident per-environment
+// state [N, S] (qpos | qvel | qacc_warmstart | mocap_pos), the episode counters that key the Philox reset
+// streams, and the launch configuration.  Everything is asynchronous on the caller's stream; no entry point
+// throws; errors come back as negative codes with a thread-local message.
+//
+// Replaces mujoco_py.load_model_from_path / MjSim / sim.step / sim.reset / sim.forward / get_state /
+// set_state as used by /root/reference/hsr/mujoco_env.py:33-34,83-94 and /root/reference/hsr/env.py:115-177.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/hsrb.h"
+#include "hsrb_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail(-2, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct hsrb {
+  HostModel<float> hm;      // host copy (pointers into hm.buf)
+  ModelT<float> dm;         // same table with device pointers
+  unsigned char* d_model = nullptr;
+  EnvCfg<float> cfg;
+  int n = 0, device = 0, S = 0;
+  unsigned long long seed = 0, env_off = 0;
+  float* d_state = nullptr;
+  unsigned* d_episode = nullptr;
+  unsigned long long* d_stats = nullptr;
+  // launch configuration
+  int lanes = 0, lanes_req = 0;
+  unsigned ws_bytes = 0;
+  int blocks_per_sm = 0, grid = 0, num_sm = 0;
+  bool configured = false;
+  // scratch for the host-buffer entry point
+  float *d_ctrl = nullptr, *d_obs = nullptr, *d_reward = nullptr;
+  unsigned char* d_done = nullptr;
+  int* d_taken = nullptr;
+  cudaStream_t host_stream = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+cudaError_t prepare(int G, size_t smem, int* bps) {
+  switch (G) {
+    case 4: return hsrb_prepare_step_4(smem, bps);
+    case 8: return hsrb_prepare_step_8(smem, bps);
+    case 16: return hsrb_prepare_step_16(smem, bps);
+    default: return hsrb_prepare_step_32(smem, bps);
+  }
+}
+cudaError_t launch(int G, const KArgs& a, int grid, size_t smem, cudaStream_t s) {
+  switch (G) {
+    case 4: return hsrb_launch_step_4(a, grid, smem, s);
+    case 8: return hsrb_launch_step_8(a, grid, smem, s);
+    case 16: return hsrb_launch_step_16(a, grid, smem, s);
+    default: return hsrb_launch_step_32(a, grid, smem, s);
+  }
+}
+
+// Choose lanes-per-environment and the grid: as many lanes per env as keeps every environment resident in
+// one wave (more lanes = shorter dependent chain per substep), otherwise fewer lanes / a grid-stride loop.
+int configure(hsrb* h) {
+  if (h->configured) return 0;
+  h->ws_bytes = (unsigned)ws_carve<float>(h->dm, nullptr, nullptr);
+  int cands[4] = {32, 16, 8, 4};
+  int best = 0;
+  for (int k = 0; k < 4; k++) {
+    int G = cands[k];
+    if (h->lanes_req && G != h->lanes_req) continue;
+    size_t smem = (size_t)h->ws_bytes * (32 / G);
+    if (smem > 227 * 1024) continue;
+    int bps = 0;
+    if (prepare(G, smem, &bps) != cudaSuccess || bps <= 0) { cudaGetLastError(); continue; }
+    long long resident = (long long)bps * h->num_sm * (32 / G);
+    best = G; h->blocks_per_sm = bps;
+    if (resident >= h->n) break;  // first (widest) G that holds every environment in one wave
+  }
+  if (!best) return fail(-3, "no launch configuration fits: workspace %u bytes per environment", h->ws_bytes);
+  h->lanes = best;
+  size_t smem = (size_t)h->ws_bytes * (32 / best);
+  CU(prepare(best, smem, &h->blocks_per_sm));
+  int gpb = 32 / best;
+  int need = (h->n + gpb - 1) / gpb;
+  int cap = h->blocks_per_sm * h->num_sm;
+  h->grid = need < cap ? need : cap;
+  if (h->grid < 1) h->grid = 1;
+  h->configured = true;
+  return 0;
+}
+
+KArgs base_args(hsrb* h) {
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.m = h->dm; a.cfg = h->cfg; a.n = h->n; a.S = h->S; a.ws_bytes = h->ws_bytes;
+  a.seed = h->seed; a.env_off = h->env_off; a.state = h->d_state; a.episode = h->d_episode; a.stats = h->d_stats;
+  return a;
+}
+
+int run(hsrb* h, KArgs& a, void* stream) {
+  int rc = configure(h);
+  if (rc) return rc;
+  a.ws_bytes = h->ws_bytes;
+  a.m.ncon_max = h->dm.ncon_max; a.m.nefc_max = h->dm.nefc_max;
+  size_t smem = (size_t)h->ws_bytes * (32 / h->lanes);
+  CU(launch(h->lanes, a, h->grid, smem, (cudaStream_t)stream));
+  h->launches++;
+  return 0;
+}
+
+__global__ void gather_state(const float* __restrict__ st, int n, int S, int off, int w, float* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * w) return;
+  int e = (int)(i / w), k = (int)(i % w);
+  out[i] = st[(size_t)e * S + off + k];
+}
+__global__ void scatter_state(float* __restrict__ st, int n, int S, int off, int w, const float* __restrict__ in) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * w) return;
+  int e = (int)(i / w), k = (int)(i % w);
+  st[(size_t)e * S + off + k] = in[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hsrb_last_error(void) { return g_err; }
+
+int hsrb_create(const void* model_blob, size_t bytes, int n_envs, int device, uint64_t seed, uint64_t env_id_offset,
+                hsrb_t** out) {
+  if (!model_blob || !out || n_envs <= 0) return fail(-1, "hsrb_create: bad arguments");
+  *out = nullptr;
+  hsrb* h = new (std::nothrow) hsrb();
+  if (!h) return fail(-1, "out of host memory");
+  std::string err;
+  if (!h->hm.parse(model_blob, bytes, err)) { delete h; return fail(-1, "model blob: %s", err.c_str()); }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    delete h;
+    return fail(-2, "no CUDA device (%s): this backend has no CPU fallback", cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) { delete h; return fail(-1, "device %d out of range (%d visible)", device, ndev); }
+  h->n = n_envs; h->device = device; h->seed = seed; h->env_off = env_id_offset;
+  h->S = h->hm.m.nq + 2 * h->hm.m.nv + 3;
+  memset(&h->cfg, 0, sizeof(h->cfg));
+  h->cfg.qidx0 = 0; h->cfg.qidx1 = 2;
+#define CUH(call)                                                                                    \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) { int rc_ = fail(-2, "%s: %s", #call, cudaGetErrorString(e_)); hsrb_destroy(h); return rc_; } \
+  } while (0)
+  CUH(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUH(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    int rc = fail(-2, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    hsrb_destroy(h);
+    return rc;
+  }
+  h->num_sm = prop.multiProcessorCount;
+  CUH(cudaMalloc(&h->d_model, h->hm.buf.size()));
+  CUH(cudaMemcpy(h->d_model, h->hm.buf.data(), h->hm.buf.size(), cudaMemcpyHostToDevice));
+  HostModel<float> tmp = h->hm;  // copy the table, then point it at the device buffer
+  tmp.rebase(h->d_model);
+  h->dm = tmp.m;
+  h->hm.rebase(h->hm.buf.data());
+  CUH(cudaMalloc(&h->d_state, sizeof(float) * (size_t)h->n * h->S));
+  CUH(cudaMalloc(&h->d_episode, sizeof(unsigned) * (size_t)h->n));
+  CUH(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * ST_COUNT));
+  CUH(cudaMemset(h->d_episode, 0, sizeof(unsigned) * (size_t)h->n));
+  CUH(cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * ST_COUNT));
+  CUH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  // state after load = mj_resetData: qpos0, zero velocities (MjSim(model), mujoco_env.py:34)
+  {
+    std::vector<float> row(h->S, 0.f);
+    for (int i = 0; i < h->hm.m.nq; i++) row[i] = h->hm.m.qpos0[i];
+    for (int k = 0; k < 3; k++) row[h->hm.m.nq + 2 * h->hm.m.nv + k] = h->hm.m.mocap_pos0[k];
+    std::vector<float> all((size_t)h->n * h->S);
+    for (int e2 = 0; e2 < h->n; e2++) memcpy(all.data() + (size_t)e2 * h->S, row.data(), sizeof(float) * h->S);
+    CUH(cudaMemcpy(h->d_state, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice));
+  }
+#undef CUH
+  *out = h;
+  return 0;
+}
+
+int hsrb_destroy(hsrb_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_episode); cudaFree(h->d_stats);
+  cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_taken);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  delete h;
+  return 0;
+}
+
+int hsrb_dims(hsrb_t* h, int* nq, int* nv, int* nu, int* nbody, int* nblock) {
+  if (!h) return fail(-1, "null handle");
+  if (nq) *nq = h->hm.m.nq;
+  if (nv) *nv = h->hm.m.nv;
+  if (nu) *nu = h->hm.m.nu;
+  if (nbody) *nbody = h->hm.m.nbody;
+  if (nblock) *nblock = h->hm.m.nblock;
+  return 0;
+}
+
+int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max) {
+  if (!h) return fail(-1, "null handle");
+  if (lanes_per_env != 0 && lanes_per_env != 4 && lanes_per_env != 8 && lanes_per_env != 16 && lanes_per_env != 32)
+    return fail(-1, "lanes_per_env must be 0, 4, 8, 16 or 32");
+  h->lanes_req = lanes_per_env;
+  if (ncon_max > 0) h->dm.ncon_max = h->hm.m.ncon_max = ncon_max;
+  if (nefc_max > 0) h->dm.nefc_max = h->hm.m.nefc_max = nefc_max;
+  h->configured = false;
+  CU(cudaSetDevice(h->device));
+  return configure(h);
+}
+
+int hsrb_set_goals(hsrb_t* h, const float* goal_lohi, const float* block_lohi, float geofence, float min_sep, int qidx0,
+                   int qidx1) {
+  if (!h) return fail(-1, "null handle");
+  if (qidx0 < 0 || qidx0 > 3 || qidx1 < 0 || qidx1 > 3) return fail(-1, "quaternion indices must be in 0..3");
+  EnvCfg<float>& c = h->cfg;
+  c.has_goal = goal_lohi ? 1 : 0;
+  c.has_block = block_lohi ? 1 : 0;
+  c.qidx0 = qidx0; c.qidx1 = qidx1; c.geofence = geofence; c.min_sep = min_sep;
+  for (int k = 0; k < 3; k++) { c.goal_lo[k] = goal_lohi ? goal_lohi[k] : 0.f; c.goal_hi[k] = goal_lohi ? goal_lohi[3 + k] : 0.f; }
+  for (int k = 0; k < 4; k++) { c.block_lo[k] = block_lohi ? block_lohi[k] : 0.f; c.block_hi[k] = block_lohi ? block_lohi[4 + k] : 0.f; }
+  return 0;
+}
+
+int hsrb_reset(hsrb_t* h, const uint8_t* mask, float* obs, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  CU(cudaSetDevice(h->device));
+  KArgs a = base_args(h);
+  a.mode = MODE_RESET; a.mask = mask; a.obs = obs; a.nsub = 0;
+  return run(h, a, stream);
+}
+
+int hsrb_step(hsrb_t* h, const float* ctrl, int nsubsteps, float* obs, float* reward, uint8_t* done, uint8_t* success,
+              int32_t* substeps_taken, uint8_t* bad_state, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  if (!ctrl && h->hm.m.nu > 0) return fail(-1, "ctrl is NULL");
+  if (nsubsteps < 0) return fail(-1, "nsubsteps < 0");
+  CU(cudaSetDevice(h->device));
+  KArgs a = base_args(h);
+  a.mode = MODE_STEP; a.ctrl = ctrl; a.nsub = nsubsteps; a.obs = obs; a.reward = reward; a.done = done;
+  a.success = success; a.taken = substeps_taken; a.bad = bad_state;
+  return run(h, a, stream);
+}
+
+int hsrb_step_host(hsrb_t* h, const float* ctrl_host, int nsubsteps, float* obs_host, float* reward_host,
+                   uint8_t* done_host, int32_t* taken_host) {
+  if (!h) return fail(-1, "null handle");
+  CU(cudaSetDevice(h->device));
+  const int n = h->n, nu = h->hm.m.nu, nobs = h->hm.m.nq + h->hm.m.nv;
+  if (!h->d_obs) {
+    CU(cudaMalloc(&h->d_ctrl, sizeof(float) * (size_t)n * (nu > 0 ? nu : 1)));
+    CU(cudaMalloc(&h->d_obs, sizeof(float) * (size_t)n * nobs));
+    CU(cudaMalloc(&h->d_reward, sizeof(float) * (size_t)n));
+    CU(cudaMalloc(&h->d_done, (size_t)n));
+    CU(cudaMalloc(&h->d_taken, sizeof(int) * (size_t)n));
+  }
+  cudaStream_t s = h->host_stream;
+  if (nu > 0) CU(cudaMemcpyAsync(h->d_ctrl, ctrl_host, sizeof(float) * (size_t)n * nu, cudaMemcpyHostToDevice, s));
+  int rc = hsrb_step(h, h->d_ctrl, nsubsteps, h->d_obs, h->d_reward, h->d_done, nullptr, h->d_taken, nullptr, s);
+  if (rc) return rc;
+  if (obs_host) CU(cudaMemcpyAsync(obs_host, h->d_obs, sizeof(float) * (size_t)n * nobs, cudaMemcpyDeviceToHost, s));
+  if (reward_host) CU(cudaMemcpyAsync(reward_host, h->d_reward, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (done_host) CU(cudaMemcpyAsync(done_host, h->d_done, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (taken_host) CU(cudaMemcpyAsync(taken_host, h->d_taken, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int hsrb_get_state(hsrb_t* h, float* qpos, float* qvel, float* qacc_warm, float* mocap_pos, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  CU(cudaSetDevice(h->device));
+  const int nq = h->hm.m.nq, nv = h->hm.m.nv;
+  float* outs[4] = {qpos, qvel, qacc_warm, mocap_pos};
+  int offs[4] = {0, nq, nq + nv, nq + 2 * nv}, ws[4] = {nq, nv, nv, 3};
+  for (int k = 0; k < 4; k++) {
+    if (!outs[k] || ws[k] == 0) continue;
+    long long tot = (long long)h->n * ws[k];
+    gather_state<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d_state, h->n, h->S, offs[k], ws[k], outs[k]);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int hsrb_set_state(hsrb_t* h, const float* qpos, const float* qvel, const float* qacc_warm, const float* mocap_pos,
+                   void* stream) {
+  if (!h) return fail(-1, "null handle");
+  CU(cudaSetDevice(h->device));
+  const int nq = h->hm.m.nq, nv = h->hm.m.nv;
+  const float* ins[4] = {qpos, qvel, qacc_warm, mocap_pos};
+  int offs[4] = {0, nq, nq + nv, nq + 2 * nv}, ws[4] = {nq, nv, nv, 3};
+  for (int k = 0; k < 4; k++) {
+    if (!ins[k] || ws[k] == 0) continue;
+    long long tot = (long long)h->n * ws[k];
+    scatter_state<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d_state, h->n, h->S, offs[k], ws[k], ins[k]);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int hsrb_forward(hsrb_t* h, float* body_xpos, float* gripper_pos, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  CU(cudaSetDevice(h->device));
+  KArgs a = base_args(h);
+  a.mode = MODE_FORWARD; a.body_xpos = body_xpos; a.gripper = gripper_pos;
+  return run(h, a, stream);
+}
+
+int hsrb_compute_reward(hsrb_t* h, float* reward, uint8_t* success, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  CU(cudaSetDevice(h->device));
+  KArgs a = base_args(h);
+  a.mode = MODE_FORWARD; a.reward = reward; a.success = success;
+  return run(h, a, stream);
+}
+
+int hsrb_debug_size(hsrb_t* h) {
+  if (!h) return fail(-1, "null handle");
+  return (int)debug_size(h->dm);
+}
+
+int hsrb_debug_substep(hsrb_t* h, const float* ctrl, double* dump, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  if (!dump) return fail(-1, "dump is NULL");
+  CU(cudaSetDevice(h->device));
+  KArgs a = base_args(h);
+  a.mode = MODE_DEBUG; a.ctrl = ctrl; a.nsub = 1; a.dump = dump; a.dump_stride = (unsigned)debug_size(h->dm);
+  return run(h, a, stream);
+}
+
+int hsrb_stats(hsrb_t* h, int64_t* out9, void* stream) {
+  if (!h || !out9) return fail(-1, "bad arguments");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  unsigned long long v[ST_COUNT];
+  CU(cudaMemcpy(v, h->d_stats, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < ST_COUNT; i++) out9[i] = (int64_t)v[i];
+  out9[ST_LAUNCHES] = h->launches;
+  return 0;
+}
+
+int hsrb_launch_info(hsrb_t* h, int* out4) {
+  if (!h || !out4) return fail(-1, "bad arguments");
+  CU(cudaSetDevice(h->device));
+  int rc = configure(h);
+  if (rc) return rc;
+  out4[0] = h->lanes; out4[1] = (int)h->ws_bytes; out4[2] = h->blocks_per_sm * (32 / h->lanes); out4[3] = h->grid;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+// Action kernel instantiated for 4 lanes per environment (see hsrb_kernels.cuh).
+#include "hsrb_kernels.cuh"
+HSRB_DEFINE_G(4)

@@ -1,0 +1,93 @@
+/* hsrb.h - C ABI of the B200 batched physics backend for hsr-env (libhsrb.so).
+ *
+ * The reference has no FFI of its own: the seam its hot path sits behind is the mujoco-py object API as used
+ * by hsr/ (SURVEY.md §8b).  Each entry point below names the reference call site(s) it replaces.  All pointers
+ * are plain device pointers owned by the caller unless the name says "host"; every call is asynchronous on
+ * the cudaStream_t passed as `stream` (0 = legacy default stream) unless it says otherwise; nothing throws:
+ * the return value is 0 on success and <0 on error, with a thread-local message from hsrb_last_error().
+ * One handle per (process, GPU); a handle is not thread-safe.  There is NO CPU fallback.
+ */
+#ifndef HSRB_H
+#define HSRB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hsrb hsrb_t;
+
+/* mujoco_py.load_model_from_path + MjSim(model)            /root/reference/hsr/mujoco_env.py:33-34
+ * model_blob: output of hsr_env_b200.model.Model.to_blob() (MJCF -> flat arrays, hsr_env_b200/mjcf.py).
+ * env_id_offset: global id of local env 0 (Philox streams are keyed on the global id, so a trajectory does
+ * not depend on how environments are sharded across ranks). */
+int hsrb_create(const void* model_blob, size_t bytes, int n_envs, int device, uint64_t seed, uint64_t env_id_offset,
+                hsrb_t** out);
+int hsrb_destroy(hsrb_t* h);
+
+/* model.nq / nv / nu (mujoco_env.py:88, 44), number of fused bodies, number of blocks (goals) */
+int hsrb_dims(hsrb_t* h, int* nq, int* nv, int* nu, int* nbody, int* nblock);
+
+/* Tuning knobs, valid before the first reset/step: lanes of a warp per environment (0 = auto from n_envs;
+ * 4, 8, 16 or 32) and the contact / constraint-row capacities (0 = model default; MuJoCo's nconmax/njmax,
+ * /root/reference/hsr/models/world.xml:44). */
+int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max);
+
+/* GoalSpec(a=block_space, b=goal_space, distance=geofence)  /root/reference/hsr/util.py:70-74, env.py:161-172
+ * goal_lohi = {lo[3], hi[3]} (NULL: goals=None, the env is never done), block_lohi = {lo[4], hi[4]} over
+ * (x, y, quat[qidx0], quat[qidx1]); min_sep > 0 rejection-samples block (x,y) at least that far apart. */
+int hsrb_set_goals(hsrb_t* h, const float* goal_lohi_host, const float* block_lohi_host, float geofence,
+                   float min_sep, int qidx0, int qidx1);
+
+/* MujocoEnv.reset + HSREnv.reset_model                      mujoco_env.py:83-85, env.py:158-177
+ * mask[N] (NULL = all): environments to reset.  obs[N, nq+nv] (nullable) receives the new observation. */
+int hsrb_reset(hsrb_t* h, const uint8_t* mask, float* obs, void* stream);
+
+/* HSREnv.step: ctrl write, <= nsubsteps x (mj_step, goal test, early break), obs/reward/done   env.py:115-135
+ * ctrl[N, nu]; obs[N, nq+nv]; reward[N] = float(success); done = success; substeps_taken[N] = executed
+ * substeps (env.py:127-131 breaks early); bad_state[N] bit flags (1 contact overflow, 2 non-finite/huge
+ * state, 4 Cholesky pivot clamp).  Any output pointer may be NULL. */
+int hsrb_step(hsrb_t* h, const float* ctrl, int nsubsteps, float* obs, float* reward, uint8_t* done, uint8_t* success,
+              int32_t* substeps_taken, uint8_t* bad_state, void* stream);
+
+/* Same call with HOST buffers (the way the reference's caller holds its numpy arrays, hsr/control.py:48-63):
+ * copies ctrl host->device, steps, copies obs/reward/done/substeps device->host and synchronises. */
+int hsrb_step_host(hsrb_t* h, const float* ctrl_host, int nsubsteps, float* obs_host, float* reward_host,
+                   uint8_t* done_host, int32_t* substeps_taken_host);
+
+/* sim.get_state / sim.set_state (+ qacc_warmstart, which MuJoCo keeps outside MjSimState)   env.py:69,150,175
+ * qpos[N,nq] qvel[N,nv] qacc_warm[N,nv] mocap_pos[N,3]; NULL pointers are skipped. */
+int hsrb_get_state(hsrb_t* h, float* qpos, float* qvel, float* qacc_warm, float* mocap_pos, void* stream);
+int hsrb_set_state(hsrb_t* h, const float* qpos, const float* qvel, const float* qacc_warm, const float* mocap_pos,
+                   void* stream);
+
+/* sim.forward + data.get_body_xpos (block_pos / gripper_pos)      env.py:176,179-186
+ * body_xpos[N, nbody, 3]; gripper_pos[N,3] = mean of the two distal finger links (nullable). */
+int hsrb_forward(hsrb_t* h, float* body_xpos, float* gripper_pos, void* stream);
+
+/* compute_reward (named by the north star; absent from the snapshot, defined as float(all in_range) to
+ * agree with env.py:126,133): reward[N] / success[N] of the CURRENT state, no stepping. */
+int hsrb_compute_reward(hsrb_t* h, float* reward, uint8_t* success, void* stream);
+
+/* Teacher-forced parity hook: one substep from the current state with per-stage outputs
+ * (xpos, M, qfrc_smooth, qacc_smooth, qacc, contacts, efc_J/D/aref/force, next qpos/qvel) as
+ * dump[N, hsrb_debug_size()] doubles, layout = hsr::debug_dump (csrc/hsr_core.h). */
+int hsrb_debug_size(hsrb_t* h);
+int hsrb_debug_substep(hsrb_t* h, const float* ctrl, double* dump, void* stream);
+
+/* Cumulative counters since creation, copied to host (synchronises `stream`):
+ * [0] substeps executed, [1] Newton iterations, [2] narrowphase calls, [3] line-search evaluations,
+ * [4] contacts (summed over substeps), [5] constraint rows (summed), [6] kernel launches, [7] environments
+ * flagged bad, [8] algorithmic flops (SURVEY.md §8(d) stage formulas with the actual per-substep counts). */
+int hsrb_stats(hsrb_t* h, int64_t* out9_host, void* stream);
+
+/* Introspection used by bench.py: lanes per env, shared-memory bytes per env, resident envs per SM, grid. */
+int hsrb_launch_info(hsrb_t* h, int* out4_host);
+
+const char* hsrb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
