@@ -288,6 +288,11 @@ def run_gpu(args):
                  "note": "algorithmic flops = SURVEY.md 8(d) stage formulas with the kernel's actual per-substep counts"},
         "episode_stats_per_rank": gathered,
     }
+    ph = {k: st1["phase_cycles"][k] - st0["phase_cycles"][k] for k in st1["phase_cycles"]}
+    if sum(ph.values()) > 0:
+        tot = float(sum(ph.values()))
+        line["phase_share"] = {k: round(v / tot, 4) for k, v in ph.items()}
+        line["phase_cycles_per_substep_lane0"] = tot / max(1.0, sub_local)
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         acts, subs, csecs, _ = cpu_port_run(max(cores * 4, 32), 1000, cores, budget_s=args.cpu_seconds)

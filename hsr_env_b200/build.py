@@ -27,22 +27,26 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, phase_clocks: bool = False) -> Path:
+    """phase_clocks=True builds the instrumented variant libhsrb_prof.so (-DHSRB_PHASE_CLOCKS)."""
     hdrs = [CSRC / h for h in HEADERS]
     objs = []
     jobs = []
+    tag = ".prof" if phase_clocks else ""
+    flags = FLAGS + (["-DHSRB_PHASE_CLOCKS"] if phase_clocks else [])
+    lib = CSRC / "libhsrb_prof.so" if phase_clocks else LIB
     for tu in TUS:
         src = CSRC / tu
-        obj = CSRC / (src.stem + ".o")
+        obj = CSRC / (src.stem + tag + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *flags, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        (CSRC / (src.stem + ".ptxas.log")).write_text(r.stderr)
+        (CSRC / (src.stem + tag + ".ptxas.log")).write_text(r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stderr}")
         return src.name, r.stderr
@@ -52,11 +56,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             for name, log in ex.map(compile_one, jobs):
                 if verbose:
                     print(f"--- {name}\n{log}")
-    if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if force or jobs or _stale(lib, objs):
+        cmd = [NVCC, "-shared", "-o", str(lib), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_clocks="--prof" in sys.argv))

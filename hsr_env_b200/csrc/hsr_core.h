@@ -26,6 +26,14 @@
 
 namespace hsr {
 
+// Geometry precision.  Body / geom poses, the narrowphase and the goal distance are evaluated in double whatever
+// the state / solver type T is: a contact distance is a difference of O(0.3 m) positions and is multiplied by the
+// contact stiffness (k ~ 5e3 s^-2) and the constraint weight before it reaches the 1 kg block whose inertia is
+// ~3e-4 kg m^2, so the 3e-8 m resolution of fp32 positions shows up as ~1 rad/s^2 in qacc.  Inputs (qpos, model
+// constants) are fp32 on the device and are exactly representable in double, so this stage has no input error.
+// It is a few hundred flops per substep; the solver (the bulk of the arithmetic) stays in T.
+using GT = double;
+
 using std::cos; using std::fabs; using std::fmax; using std::fmin; using std::pow; using std::sin; using std::sqrt;
 
 template <typename T> struct Lim;
@@ -40,7 +48,23 @@ template <> struct Lim<double> {
 
 enum { FLAG_CON_OVERFLOW = 1, FLAG_BAD_NUM = 2, FLAG_CHOL = 4 };
 enum { WI_NCON = 0, WI_NEFC = 1, WI_NLIMIT = 2, WI_FLAGS = 3, WI_ITER = 4, WI_NARROW = 5, WI_LSEVAL = 6, WI_KFLOP = 7,
-       WI_SUMCON = 8, WI_SUMEFC = 9, WI_NPFLOP = 10, WI_COUNT = 12 };
+       WI_SUMCON = 8, WI_SUMEFC = 9, WI_NPFLOP = 10, WI_TLAST = 11, WI_PHASE0 = 12, WI_COUNT = 20 };
+enum { PH_KIN = 0, PH_CRB, PH_SMOOTH, PH_COLLIDE, PH_ROWS, PH_SOLVE, PH_EULER, PH_COUNT };
+// per-phase cycle counters (lane 0, clock64), compiled in only with -DHSRB_PHASE_CLOCKS (tools/gpu_phases.sh)
+#if defined(HSRB_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define HSR_PHASE(w, g, id)                                                             \
+  do {                                                                                  \
+    if ((g).lane == 0) {                                                                \
+      int t_ = (int)clock64();                                                          \
+      (w).wi[WI_PHASE0 + (id)] += (t_ - (w).wi[WI_TLAST]) >> 4;                         \
+      (w).wi[WI_TLAST] = t_;                                                            \
+    }                                                                                   \
+  } while (0)
+#define HSR_PHASE_START(w, g) do { if ((g).lane == 0) (w).wi[WI_TLAST] = (int)clock64(); } while (0)
+#else
+#define HSR_PHASE(w, g, id) do { } while (0)
+#define HSR_PHASE_START(w, g) do { } while (0)
+#endif
 #define HSR_LSQ 10
 
 // ------------------------------------------------------------------------------------------------ groups
@@ -91,6 +115,9 @@ struct DevGrp {
 template <typename T> struct V3 { T x, y, z; };
 template <typename T> HSR_HD V3<T> mk(T x, T y, T z) { V3<T> v; v.x = x; v.y = y; v.z = z; return v; }
 template <typename T> HSR_HD V3<T> ld3(const T* p) { return mk<T>(p[0], p[1], p[2]); }
+template <typename T> HSR_HD V3<GT> ldg(const T* p) { return mk<GT>((GT)p[0], (GT)p[1], (GT)p[2]); }
+template <typename T, typename U> HSR_HD V3<T> cvt(V3<U> v) { return mk<T>((T)v.x, (T)v.y, (T)v.z); }
+template <typename T, typename U> HSR_HD void st3c(T* p, V3<U> v) { p[0] = (T)v.x; p[1] = (T)v.y; p[2] = (T)v.z; }
 template <typename T> HSR_HD void st3(T* p, V3<T> v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 template <typename T> HSR_HD V3<T> operator+(V3<T> a, V3<T> b) { return mk<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
 template <typename T> HSR_HD V3<T> operator-(V3<T> a, V3<T> b) { return mk<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -140,12 +167,12 @@ template <typename T> HSR_HD void quatnormalize(T* q) {
 // ------------------------------------------------------------------------------------------------ workspace
 template <typename T>
 struct WS {
+  GT *xpos, *xquat, *xmat, *xipos, *anchor, *axis, *gpos, *com;
   T *qpos, *qvel, *warm, *ctrl, *mocap;
-  T *xpos, *xquat, *xmat, *xipos, *anchor, *axis;
   T *cdof, *cinert, *binert;
   T *M, *L, *H;
   T *qfrc_smooth, *qacc_smooth, *qacc, *Ma, *grad, *search, *Mv, *tmpv;
-  T *gpos, *gaabb;
+  T *gaabb;
   T *con_dist, *con_pos, *con_frame, *con_mu;
   T *J, *W, *D, *aref, *jar, *jv, *force;
   T *lsq;
@@ -161,14 +188,14 @@ HSR_HD size_t ws_carve(const ModelT<T>& m, WS<T>* w, unsigned char* base) {
   if (!w) w = &dummy;
 #define CARVE(field, type, n) { w->field = (type*)(base + off); off += sizeof(type) * (size_t)(n); }
   int nv = m.nv, nb = m.nbody, nc = m.ncon_max, ne = m.nefc_max;
+  CARVE(xpos, GT, nb * 3) CARVE(xquat, GT, nb * 4) CARVE(xmat, GT, nb * 9) CARVE(xipos, GT, nb * 3)
+  CARVE(anchor, GT, m.njnt * 3) CARVE(axis, GT, m.njnt * 3) CARVE(gpos, GT, m.ngeom * 3) CARVE(com, GT, nb * 3)
   CARVE(qpos, T, m.nq) CARVE(qvel, T, nv) CARVE(warm, T, nv) CARVE(ctrl, T, m.nu > 0 ? m.nu : 1) CARVE(mocap, T, 3)
-  CARVE(xpos, T, nb * 3) CARVE(xquat, T, nb * 4) CARVE(xmat, T, nb * 9) CARVE(xipos, T, nb * 3)
-  CARVE(anchor, T, m.njnt * 3) CARVE(axis, T, m.njnt * 3)
   CARVE(cdof, T, nv * 6) CARVE(cinert, T, nb * 10) CARVE(binert, T, nb * 10)
   CARVE(M, T, nv * nv) CARVE(L, T, nv * nv) CARVE(H, T, nv * nv)
   CARVE(qfrc_smooth, T, nv) CARVE(qacc_smooth, T, nv) CARVE(qacc, T, nv) CARVE(Ma, T, nv) CARVE(grad, T, nv)
   CARVE(search, T, nv) CARVE(Mv, T, nv) CARVE(tmpv, T, nv)
-  CARVE(gpos, T, m.ngeom * 3) CARVE(gaabb, T, m.ngeom * 3)
+  CARVE(gaabb, T, m.ngeom * 3)
   CARVE(con_dist, T, nc) CARVE(con_pos, T, nc * 3) CARVE(con_frame, T, nc * 9) CARVE(con_mu, T, nc)
   CARVE(J, T, ne * nv) CARVE(W, T, ne * nv) CARVE(D, T, ne) CARVE(aref, T, ne) CARVE(jar, T, ne) CARVE(jv, T, ne)
   CARVE(force, T, ne) CARVE(lsq, T, nc * HSR_LSQ)
@@ -179,7 +206,7 @@ HSR_HD size_t ws_carve(const ModelT<T>& m, WS<T>* w, unsigned char* base) {
 }
 
 // ------------------------------------------------------------------------------------------------ B.1 kinematics
-// 10-number spatial inertia about the world origin: Ixx Iyy Izz Ixy Ixz Iyz  m*cx m*cy m*cz  m
+// 10-number spatial inertia about the reference point (tree CoM): Ixx Iyy Izz Ixy Ixz Iyz  m*cx m*cy m*cz  m
 template <typename T> HSR_HD void inert_mul(const T* I, const T* v, T* f) {  // f = I * v,  v=[ang;lin], f=[torque;force]
   V3<T> w = ld3(v), vo = ld3(v + 3), mc = ld3(I + 6);
   V3<T> fl = vo * I[9] + cross(w, mc);
@@ -192,38 +219,40 @@ template <typename T>
 HSR_HD void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
   // world
   for (int k = 0; k < 3; k++) { w.xpos[k] = 0; w.xipos[k] = 0; }
-  for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? T(1) : T(0);
+  for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? GT(1) : GT(0);
   w.xquat[0] = 1; w.xquat[1] = w.xquat[2] = w.xquat[3] = 0;
   for (int k = 0; k < 10; k++) { w.binert[k] = 0; }
   for (int b = 1; b < m.nbody; b++) {
     int p = m.body_parent[b];
     int j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
-    T pos[3], quat[4], R[9];
+    GT pos[3], quat[4], R[9];
     if (nj == 1 && m.jnt_type[j0] == JNT_FREE) {
       int a = m.jnt_qposadr[j0];
-      quatnormalize(w.qpos + a + 3);
-      for (int k = 0; k < 3; k++) pos[k] = w.qpos[a + k];
-      for (int k = 0; k < 4; k++) quat[k] = w.qpos[a + 3 + k];
+      for (int k = 0; k < 3; k++) pos[k] = (GT)w.qpos[a + k];
+      for (int k = 0; k < 4; k++) quat[k] = (GT)w.qpos[a + 3 + k];
+      quatnormalize(quat);
+      for (int k = 0; k < 4; k++) w.qpos[a + 3 + k] = (T)quat[k];  // MuJoCo normalises qpos in place
       for (int k = 0; k < 3; k++) w.anchor[3 * j0 + k] = pos[k];
       quat2mat(quat, R);
     } else {
-      V3<T> pp = ld3(w.xpos + 3 * p) + mulv(w.xmat + 9 * p, ld3(m.body_pos + 3 * b));
+      V3<GT> pp = ld3(w.xpos + 3 * p) + mulv(w.xmat + 9 * p, ldg(m.body_pos + 3 * b));
       st3(pos, pp);
-      quatmul(w.xquat + 4 * p, m.body_quat + 4 * b, quat);
+      GT bq[4] = {(GT)m.body_quat[4 * b], (GT)m.body_quat[4 * b + 1], (GT)m.body_quat[4 * b + 2], (GT)m.body_quat[4 * b + 3]};
+      quatmul(w.xquat + 4 * p, bq, quat);
       quat2mat(quat, R);
       for (int j = j0; j < j0 + nj; j++) {
-        V3<T> anc = ld3(pos) + mulv(R, ld3(m.jnt_pos + 3 * j));
-        V3<T> ax = mulv(R, ld3(m.jnt_axis + 3 * j));
+        V3<GT> anc = ld3(pos) + mulv(R, ldg(m.jnt_pos + 3 * j));
+        V3<GT> ax = mulv(R, ldg(m.jnt_axis + 3 * j));
         st3(w.anchor + 3 * j, anc); st3(w.axis + 3 * j, ax);
-        T q = w.qpos[m.jnt_qposadr[j]] - m.qpos0[m.jnt_qposadr[j]];
+        GT q = (GT)w.qpos[m.jnt_qposadr[j]] - (GT)m.qpos0[m.jnt_qposadr[j]];
         if (m.jnt_type[j] == JNT_SLIDE) {
           st3(pos, ld3(pos) + ax * q);
         } else {
-          T h = q * T(0.5), s = sin(h);
-          T dq[4] = {cos(h), s * m.jnt_axis[3 * j], s * m.jnt_axis[3 * j + 1], s * m.jnt_axis[3 * j + 2]};
+          GT h = q * GT(0.5), sn = sin(h);
+          GT dq[4] = {cos(h), sn * (GT)m.jnt_axis[3 * j], sn * (GT)m.jnt_axis[3 * j + 1], sn * (GT)m.jnt_axis[3 * j + 2]};
           quatmul(quat, dq, quat);
           quat2mat(quat, R);
-          st3(pos, anc - mulv(R, ld3(m.jnt_pos + 3 * j)));
+          st3(pos, anc - mulv(R, ldg(m.jnt_pos + 3 * j)));
         }
       }
       quatnormalize(quat);
@@ -232,14 +261,35 @@ HSR_HD void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
     for (int k = 0; k < 3; k++) w.xpos[3 * b + k] = pos[k];
     for (int k = 0; k < 4; k++) w.xquat[4 * b + k] = quat[k];
     for (int k = 0; k < 9; k++) w.xmat[9 * b + k] = R[k];
-    V3<T> c = ld3(pos) + mulv(R, ld3(m.body_ipos + 3 * b));
-    st3(w.xipos + 3 * b, c);
-    // spatial inertia about the world origin
+    V3<GT> cg = ld3(pos) + mulv(R, ldg(m.body_ipos + 3 * b));
+    st3(w.xipos + 3 * b, cg);
+  }
+  // Centre of mass of every kinematic tree.  All spatial quantities of a tree (motion axes, inertias, bias forces,
+  // contact Jacobians) are expressed about its CoM instead of the world origin, as MuJoCo does: about the origin
+  // the parallel-axis term m |c|^2 (4e-2 for a block 0.2 m away) swamps the block's own 3e-4 kg m^2 inertia and
+  // fp32 loses 1e-5 of it.  The two formulations are the same mathematics.
+  for (int b = 0; b < m.nbody; b++) { w.com[3 * b] = 0; w.com[3 * b + 1] = 0; w.com[3 * b + 2] = 0; }
+  for (int r = 1; r < m.nbody; r++) {
+    if (m.body_root[r] != r) continue;
+    V3<GT> acc = mk<GT>(0, 0, 0);
+    GT mt = 0;
+    for (int b = r; b < m.nbody; b++)
+      if (m.body_root[b] == r) { acc = acc + ld3(w.xipos + 3 * b) * (GT)m.body_mass[b]; mt += (GT)m.body_mass[b]; }
+    if (mt > 0) acc = acc * (GT(1) / mt);
+    for (int b = r; b < m.nbody; b++)
+      if (m.body_root[b] == r) st3(w.com + 3 * b, acc);
+  }
+  for (int b = 1; b < m.nbody; b++) {
+    // spatial inertia about the tree CoM (solver precision)
+    const GT* R = w.xmat + 9 * b;
+    V3<T> c = cvt<T>(ld3(w.xipos + 3 * b) - ld3(w.com + 3 * b));
+    T Rt_[9];
+    for (int k = 0; k < 9; k++) Rt_[k] = (T)R[k];
     const T* ib = m.body_inertia + 6 * b;
     T Ib[9] = {ib[0], ib[3], ib[4], ib[3], ib[1], ib[5], ib[4], ib[5], ib[2]};
     T tmp[9], Iw[9], Rt[9];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
-    mulm(R, Ib, tmp); mulm(tmp, Rt, Iw);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rt[3 * i + j] = Rt_[3 * j + i];
+    mulm(Rt_, Ib, tmp); mulm(tmp, Rt, Iw);
     T mass = m.body_mass[b];
     T cc = dot(c, c);
     T* I = w.binert + 10 * b;
@@ -255,35 +305,37 @@ HSR_HD void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
   }
 }
 
-// B.2 (part): motion axes about the world origin, [ang; lin]; geom centres + world AABB half extents
+// B.2 (part): motion axes about the tree CoM, [ang; lin]; geom centres + world AABB half extents
 template <typename T, typename Grp>
 HSR_HD void cdof_geoms(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   for (int j = g.lane; j < m.njnt; j += Grp::G) {
     int a = m.jnt_dofadr[j], b = m.jnt_body[j], t = m.jnt_type[j];
     if (t == JNT_FREE) {
-      V3<T> xp = ld3(w.xpos + 3 * b);
+      V3<GT> xp = ld3(w.xpos + 3 * b) - ld3(w.com + 3 * b);
       for (int k = 0; k < 3; k++) {
         T* c = w.cdof + 6 * (a + k);
         for (int i = 0; i < 6; i++) c[i] = (i == 3 + k) ? T(1) : T(0);
-        V3<T> ax = mcol(w.xmat + 9 * b, k);
+        V3<GT> ax = mcol(w.xmat + 9 * b, k);
         T* cr = w.cdof + 6 * (a + 3 + k);
-        st3(cr, ax); st3(cr + 3, cross(xp, ax));
+        st3c(cr, ax); st3c(cr + 3, cross(xp, ax));
       }
     } else if (t == JNT_SLIDE) {
       T* c = w.cdof + 6 * a;
-      c[0] = c[1] = c[2] = 0; st3(c + 3, ld3(w.axis + 3 * j));
+      c[0] = c[1] = c[2] = 0; st3c(c + 3, ld3(w.axis + 3 * j));
     } else {
       T* c = w.cdof + 6 * a;
-      V3<T> ax = ld3(w.axis + 3 * j);
-      st3(c, ax); st3(c + 3, cross(ld3(w.anchor + 3 * j), ax));
+      V3<GT> ax = ld3(w.axis + 3 * j);
+      st3c(c, ax); st3c(c + 3, cross(ld3(w.anchor + 3 * j) - ld3(w.com + 3 * b), ax));
     }
   }
   for (int gi = g.lane; gi < m.ngeom; gi += Grp::G) {
     int b = m.geom_body[gi];
-    const T* R = w.xmat + 9 * b;
-    st3(w.gpos + 3 * gi, ld3(w.xpos + 3 * b) + mulv(R, ld3(m.geom_pos + 3 * gi)));
-    T Rg[9];
-    mulm(R, m.geom_mat + 9 * gi, Rg);
+    const GT* R = w.xmat + 9 * b;
+    st3(w.gpos + 3 * gi, ld3(w.xpos + 3 * b) + mulv(R, ldg(m.geom_pos + 3 * gi)));
+    // conservative world AABB half extents (midphase cull only): solver precision
+    T Rb[9], Rg[9];
+    for (int k = 0; k < 9; k++) Rb[k] = (T)R[k];
+    mulm(Rb, m.geom_mat + 9 * gi, Rg);
     const T* h = m.geom_aabb + 3 * gi;
     for (int i = 0; i < 3; i++)
       w.gaabb[3 * gi + i] = fabs(Rg[3 * i]) * h[0] + fabs(Rg[3 * i + 1]) * h[1] + fabs(Rg[3 * i + 2]) * h[2];
@@ -410,7 +462,7 @@ HSR_HD void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
 
 // ------------------------------------------------------------------------------------------------ B.3 collision
 template <typename T> struct Geom {
-  int type; const T* size; const T* verts; int nvert; V3<T> pos; T mat[9];
+  int type; const T* size; const T* verts; int nvert; V3<GT> pos; GT mat[9];
 };
 
 template <typename T>
@@ -418,50 +470,29 @@ HSR_HD void load_geom(const ModelT<T>& m, const WS<T>& w, int gi, Geom<T>& ge) {
   ge.type = m.geom_type[gi]; ge.size = m.geom_size + 3 * gi;
   ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
   ge.pos = ld3(w.gpos + 3 * gi);
-  mulm(w.xmat + 9 * m.geom_body[gi], m.geom_mat + 9 * gi, ge.mat);
+  GT gm[9];
+  for (int k = 0; k < 9; k++) gm[k] = (GT)m.geom_mat[9 * gi + k];
+  mulm(w.xmat + 9 * m.geom_body[gi], gm, ge.mat);
 }
 
-// support point in world direction d (mjccd_support, margin 0); hull vertices are scanned by all lanes
-template <typename T, typename Grp>
-HSR_HD V3<T> support(const Geom<T>& ge, V3<T> d, const Grp& g) {
-  V3<T> dl = multv(ge.mat, d), res;
-  if (ge.type == GEOM_BOX) {
-    res = mk<T>(dl.x >= 0 ? ge.size[0] : -ge.size[0], dl.y >= 0 ? ge.size[1] : -ge.size[1],
-                dl.z >= 0 ? ge.size[2] : -ge.size[2]);
-  } else if (ge.type == GEOM_CYLINDER) {
-    T n = sqrt(dl.x * dl.x + dl.y * dl.y);
-    res = mk<T>(0, 0, dl.z >= 0 ? ge.size[1] : -ge.size[1]);
-    if (n > Lim<T>::minval()) { res.x = dl.x / n * ge.size[0]; res.y = dl.y / n * ge.size[0]; }
-  } else {
-    T best = -FLT_MAX; int bi = 0x7fffffff;
-    for (int i = g.lane; i < ge.nvert; i += Grp::G) {
-      T v = ge.verts[3 * i] * dl.x + ge.verts[3 * i + 1] * dl.y + ge.verts[3 * i + 2] * dl.z;
-      if (v > best) { best = v; bi = i; }
-    }
-    g.argmax(best, bi);
-    res = ld3(ge.verts + 3 * bi);
-  }
-  return ge.pos + mulv(ge.mat, res);
-}
-
-template <typename T> HSR_HD void make_frame(V3<T> n, T* fr) {
+template <typename T> HSR_HD void make_frame(V3<GT> n, T* fr) {
   n = normalized(n);
-  V3<T> t = (n.y > T(-0.5) && n.y < T(0.5)) ? mk<T>(0, 1, 0) : mk<T>(0, 0, 1);
+  V3<GT> t = (n.y > GT(-0.5) && n.y < GT(0.5)) ? mk<GT>(0, 1, 0) : mk<GT>(0, 0, 1);
   t = t - n * dot(n, t);
   t = normalized(t);
-  st3(fr, n); st3(fr + 3, t); st3(fr + 6, cross(n, t));
+  st3c(fr, n); st3c(fr + 3, t); st3c(fr + 6, cross(n, t));
 }
 
 template <typename T, typename Grp>
-HSR_HD void add_contact(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, T dist, V3<T> pos,
-                        V3<T> n) {
+HSR_HD void add_contact(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, GT dist, V3<GT> pos,
+                        V3<GT> n) {
   int dim = m.pair_condim[pair];
   if (ncon >= m.ncon_max || nrow + dim > m.nefc_max) {
     if (g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CON_OVERFLOW;
     return;
   }
   if (g.lane == 0) {
-    w.con_pair[ncon] = pair; w.con_dist[ncon] = dist; st3(w.con_pos + 3 * ncon, pos);
+    w.con_pair[ncon] = pair; w.con_dist[ncon] = (T)dist; st3c(w.con_pos + 3 * ncon, pos);
     make_frame(n, w.con_frame + 9 * ncon);
     w.con_adr[ncon] = nrow;
   }
@@ -499,45 +530,80 @@ template <typename T> HSR_HD T origin_tri_dist2(V3<T> a, V3<T> b, V3<T> c, V3<T>
   return dot(q, q);
 }
 
+// Support point for the portal refinement, evaluated in double whatever T is: the decisions of the refinement
+// compare triple products of vectors that shrink with the penetration depth against libccd's DBL_EPSILON-scale
+// thresholds, which fp32 cannot resolve (a 0.1 mm contact came out with a different face normal).  Only the
+// vertex scan of a hull (the bulk of the work) runs in T; its result is an index, i.e. exact.
+template <typename T, typename Grp>
+HSR_HD V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
+  typedef double W;
+  const W* R = ge.mat;
+  V3<W> dl = multv(R, d), res;
+  if (ge.type == GEOM_BOX) {
+    res = mk<W>(dl.x >= 0 ? (W)ge.size[0] : -(W)ge.size[0], dl.y >= 0 ? (W)ge.size[1] : -(W)ge.size[1],
+                dl.z >= 0 ? (W)ge.size[2] : -(W)ge.size[2]);
+  } else if (ge.type == GEOM_CYLINDER) {
+    W n = sqrt(dl.x * dl.x + dl.y * dl.y);
+    res = mk<W>(0, 0, dl.z >= 0 ? (W)ge.size[1] : -(W)ge.size[1]);
+    if (n > 1e-15) { res.x = dl.x / n * (W)ge.size[0]; res.y = dl.y / n * (W)ge.size[0]; }
+  } else {
+    T lx = (T)dl.x, ly = (T)dl.y, lz = (T)dl.z;
+    T best = -FLT_MAX; int bi = 0x7fffffff;
+    for (int i = g.lane; i < ge.nvert; i += Grp::G) {
+      T v = ge.verts[3 * i] * lx + ge.verts[3 * i + 1] * ly + ge.verts[3 * i + 2] * lz;
+      if (v > best) { best = v; bi = i; }
+    }
+    g.argmax(best, bi);
+    res = mk<W>((W)ge.verts[3 * bi], (W)ge.verts[3 * bi + 1], (W)ge.verts[3 * bi + 2]);
+  }
+  return ge.pos + mulv(R, res);
+}
+
 // Minkowski Portal Refinement penetration query (libccd ccdMPRPenetration as used by mjc_Convex).
 template <typename T, typename Grp>
-HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, T tol, int max_iter, const Grp& g, T& depth,
-                             V3<T>& pdir, V3<T>& ppos) {
-  auto sup = [&](V3<T> d) { Sup<T> s; s.v1 = support(g1, d, g); s.v2 = support(g2, -d, g); s.v = s.v1 - s.v2; return s; };
-  auto reach_tol = [&](const Sup<T>& v1, const Sup<T>& v2, const Sup<T>& v3, const Sup<T>& v4, V3<T> d) {
-    T dv4 = dot(v4.v, d);
-    T d1 = dv4 - dot(v1.v, d), d2 = dv4 - dot(v2.v, d), d3 = dv4 - dot(v3.v, d);
-    T mn = fmin(d1, fmin(d2, d3));
+HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,
+                             V3<GT>& pdir_, V3<GT>& ppos_) {
+  typedef double W;
+  auto sup = [&](V3<W> d) { Sup<W> s; s.v1 = support_d(g1, d, g); s.v2 = support_d(g2, -d, g); s.v = s.v1 - s.v2; return s; };
+  auto reach_tol = [&](const Sup<W>& v1, const Sup<W>& v2, const Sup<W>& v3, const Sup<W>& v4, V3<W> d) {
+    W dv4 = dot(v4.v, d);
+    W d1 = dv4 - dot(v1.v, d), d2 = dv4 - dot(v2.v, d), d3 = dv4 - dot(v3.v, d);
+    W mn = fmin(d1, fmin(d2, d3));
     return ccd_eq(mn, tol) || mn < tol;
   };
-  auto expand = [&](const Sup<T>& v0, Sup<T>& v1, Sup<T>& v2, Sup<T>& v3, const Sup<T>& v4) {
-    V3<T> v4v0 = cross(v4.v, v0.v);
+  auto expand = [&](const Sup<W>& v0, Sup<W>& v1, Sup<W>& v2, Sup<W>& v3, const Sup<W>& v4) {
+    V3<W> v4v0 = cross(v4.v, v0.v);
     if (dot(v1.v, v4v0) > 0) {
       if (dot(v2.v, v4v0) > 0) v1 = v4; else v3 = v4;
     } else {
       if (dot(v3.v, v4v0) > 0) v2 = v4; else v1 = v4;
     }
   };
-  const T eps = Lim<T>::eps();
-  Sup<T> v0, v1, v2, v3, v4;
-  v0.v1 = g1.pos; v0.v2 = g2.pos; v0.v = v0.v1 - v0.v2;
+  auto finish = [&](W depth, V3<W> dir, V3<W> pos) {
+    depth_ = depth; pdir_ = dir; ppos_ = pos;
+    return true;
+  };
+  const W eps = Lim<W>::eps();
+  Sup<W> v0, v1, v2, v3, v4;
+  v0.v1 = g1.pos; v0.v2 = g2.pos;
+  v0.v = v0.v1 - v0.v2;
   if (fabs(v0.v.x) < eps && fabs(v0.v.y) < eps && fabs(v0.v.z) < eps) v0.v.x += eps * 10;
-  V3<T> d = normalized(-v0.v);
+  V3<W> d = normalized(-v0.v);
   v1 = sup(d);
-  T dt = dot(v1.v, d);
+  W dt = dot(v1.v, d);
   if (is_zero(dt) || dt < 0) return false;
   d = cross(v0.v, v1.v);
   if (is_zero(dot(d, d))) {
     if (fabs(v1.v.x) < eps && fabs(v1.v.y) < eps && fabs(v1.v.z) < eps) return false;
-    depth = norm(v1.v); pdir = v1.v * (T(1) / depth); ppos = (v1.v1 + v1.v2) * T(0.5);
-    return true;
+    W dep = norm(v1.v);
+    return finish(dep, v1.v * (W(1) / dep), (v1.v1 + v1.v2) * W(0.5));
   }
   d = normalized(d);
   v2 = sup(d);
   dt = dot(v2.v, d);
   if (is_zero(dt) || dt < 0) return false;
   d = normalized(cross(v1.v - v0.v, v2.v - v0.v));
-  if (dot(d, v0.v) > 0) { Sup<T> t = v1; v1 = v2; v2 = t; d = -d; }
+  if (dot(d, v0.v) > 0) { Sup<W> t = v1; v1 = v2; v2 = t; d = -d; }
   for (int guard = 0; guard < 64; guard++) {
     v3 = sup(d);
     dt = dot(v3.v, d);
@@ -568,23 +634,22 @@ HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, T tol, int ma
     d = normalized(cross(v2.v - v1.v, v3.v - v1.v));
     v4 = sup(d);
     if (reach_tol(v1, v2, v3, v4, d) || it > max_iter) {
-      V3<T> q;
-      T d2 = origin_tri_dist2(v1.v, v2.v, v3.v, q);
-      depth = sqrt(d2);
-      if (is_zero(depth)) return false;
-      pdir = q * (T(1) / norm(q));
-      T b0 = dot(cross(v1.v, v2.v), v3.v), b1 = dot(cross(v3.v, v2.v), v0.v), b2 = dot(cross(v0.v, v1.v), v3.v),
+      V3<W> q;
+      W d2 = origin_tri_dist2(v1.v, v2.v, v3.v, q);
+      W dep = sqrt(d2);
+      if (is_zero(dep)) return false;
+      V3<W> dir = q * (W(1) / norm(q));
+      W b0 = dot(cross(v1.v, v2.v), v3.v), b1 = dot(cross(v3.v, v2.v), v0.v), b2 = dot(cross(v0.v, v1.v), v3.v),
         b3 = dot(cross(v2.v, v1.v), v0.v);
-      T s = b0 + b1 + b2 + b3;
+      W s = b0 + b1 + b2 + b3;
       if (is_zero(s) || s < 0) {
         b0 = 0; b1 = dot(cross(v2.v, v3.v), d); b2 = dot(cross(v3.v, v1.v), d); b3 = dot(cross(v1.v, v2.v), d);
         s = b1 + b2 + b3;
       }
-      T inv = T(1) / s;
-      V3<T> p1 = (v0.v1 * b0 + v1.v1 * b1 + v2.v1 * b2 + v3.v1 * b3) * inv;
-      V3<T> p2 = (v0.v2 * b0 + v1.v2 * b1 + v2.v2 * b2 + v3.v2 * b3) * inv;
-      ppos = (p1 + p2) * T(0.5);
-      return true;
+      W inv = W(1) / s;
+      V3<W> p1 = (v0.v1 * b0 + v1.v1 * b1 + v2.v1 * b2 + v3.v1 * b3) * inv;
+      V3<W> p2 = (v0.v2 * b0 + v1.v2 * b1 + v2.v2 * b2 + v3.v2 * b3) * inv;
+      return finish(dep, dir, (p1 + p2) * W(0.5));
     }
     expand(v0, v1, v2, v3, v4);
     it++;
@@ -595,81 +660,82 @@ HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, T tol, int ma
 template <typename T, typename Grp>
 HSR_HDN void box_box(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, const Geom<T>& A,
                      const Geom<T>& B) {
-  const T* R1 = A.mat; const T* R2 = B.mat; const T* s1 = A.size; const T* s2 = B.size;
-  V3<T> p1 = A.pos, p2 = B.pos, d = p2 - p1;
-  T C[9], Q[9];
+  const GT* R1 = A.mat; const GT* R2 = B.mat;
+  const GT s1[3] = {(GT)A.size[0], (GT)A.size[1], (GT)A.size[2]}, s2[3] = {(GT)B.size[0], (GT)B.size[1], (GT)B.size[2]};
+  V3<GT> p1 = A.pos, p2 = B.pos, d = p2 - p1;
+  GT C[9], Q[9];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-    C[3 * i + j] = dot(mcol(R1, i), mcol(R2, j)); Q[3 * i + j] = fabs(C[3 * i + j]) + T(1e-10);
+    C[3 * i + j] = dot(mcol(R1, i), mcol(R2, j)); Q[3 * i + j] = fabs(C[3 * i + j]) + GT(1e-10);
   }
-  V3<T> dl1 = multv(R1, d), dl2 = multv(R2, d);
-  T best = -FLT_MAX; int code = -1; V3<T> n = mk<T>(0, 0, 1);
+  V3<GT> dl1 = multv(R1, d), dl2 = multv(R2, d);
+  GT best = -FLT_MAX; int code = -1; V3<GT> n = mk<GT>(0, 0, 1);
   for (int i = 0; i < 3; i++) {
-    T dd = comp(dl1, i);
-    T sep = fabs(dd) - (s1[i] + Q[3 * i] * s2[0] + Q[3 * i + 1] * s2[1] + Q[3 * i + 2] * s2[2]);
+    GT dd = comp(dl1, i);
+    GT sep = fabs(dd) - (s1[i] + Q[3 * i] * s2[0] + Q[3 * i + 1] * s2[1] + Q[3 * i + 2] * s2[2]);
     if (sep > 0) return;
-    if (sep > best) { best = sep; code = i; n = mcol(R1, i) * (dd >= 0 ? T(1) : T(-1)); }
+    if (sep > best) { best = sep; code = i; n = mcol(R1, i) * (dd >= 0 ? GT(1) : GT(-1)); }
   }
   for (int i = 0; i < 3; i++) {
-    T dd = comp(dl2, i);
-    T sep = fabs(dd) - (s2[i] + Q[i] * s1[0] + Q[3 + i] * s1[1] + Q[6 + i] * s1[2]);
+    GT dd = comp(dl2, i);
+    GT sep = fabs(dd) - (s2[i] + Q[i] * s1[0] + Q[3 + i] * s1[1] + Q[6 + i] * s1[2]);
     if (sep > 0) return;
-    if (sep > best) { best = sep; code = 3 + i; n = mcol(R2, i) * (dd >= 0 ? T(1) : T(-1)); }
+    if (sep > best) { best = sep; code = 3 + i; n = mcol(R2, i) * (dd >= 0 ? GT(1) : GT(-1)); }
   }
-  T ebest = -FLT_MAX; int ecode = -1; V3<T> en = n;
+  GT ebest = -FLT_MAX; int ecode = -1; V3<GT> en = n;
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-    V3<T> ax = cross(mcol(R1, i), mcol(R2, j));
-    T ln = norm(ax);
-    if (ln < T(1e-4)) continue;
-    ax = ax * (T(1) / ln);
+    V3<GT> ax = cross(mcol(R1, i), mcol(R2, j));
+    GT ln = norm(ax);
+    if (ln < GT(1e-4)) continue;
+    ax = ax * (GT(1) / ln);
     int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-    T ra = s1[i1] * fabs(dot(mcol(R1, i1), ax)) + s1[i2] * fabs(dot(mcol(R1, i2), ax));
-    T rb = s2[j1] * fabs(dot(mcol(R2, j1), ax)) + s2[j2] * fabs(dot(mcol(R2, j2), ax));
-    T dd = dot(d, ax);
-    T sep = fabs(dd) - (ra + rb);
+    GT ra = s1[i1] * fabs(dot(mcol(R1, i1), ax)) + s1[i2] * fabs(dot(mcol(R1, i2), ax));
+    GT rb = s2[j1] * fabs(dot(mcol(R2, j1), ax)) + s2[j2] * fabs(dot(mcol(R2, j2), ax));
+    GT dd = dot(d, ax);
+    GT sep = fabs(dd) - (ra + rb);
     if (sep > 0) return;
-    if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; en = ax * (dd >= 0 ? T(1) : T(-1)); }
+    if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; en = ax * (dd >= 0 ? GT(1) : GT(-1)); }
   }
-  if (ecode >= 0 && T(1.05) * ebest > best) { best = ebest; code = ecode; n = en; }
+  if (ecode >= 0 && GT(1.05) * ebest > best) { best = ebest; code = ecode; n = en; }
   if (code >= 6) {
     int i = (code - 6) / 3, j = (code - 6) % 3;
-    V3<T> pa = p1, pb = p2;
+    V3<GT> pa = p1, pb = p2;
     for (int k = 0; k < 3; k++) {
-      if (k != i) pa = pa + mcol(R1, k) * (s1[k] * (dot(mcol(R1, k), n) > 0 ? T(1) : T(-1)));
-      if (k != j) pb = pb - mcol(R2, k) * (s2[k] * (dot(mcol(R2, k), n) > 0 ? T(1) : T(-1)));
+      if (k != i) pa = pa + mcol(R1, k) * (s1[k] * (dot(mcol(R1, k), n) > 0 ? GT(1) : GT(-1)));
+      if (k != j) pb = pb - mcol(R2, k) * (s2[k] * (dot(mcol(R2, k), n) > 0 ? GT(1) : GT(-1)));
     }
-    V3<T> ua = mcol(R1, i), ub = mcol(R2, j), ww = pa - pb;
-    T a_ = dot(ua, ua), b_ = dot(ua, ub), c_ = dot(ub, ub), d_ = dot(ua, ww), e_ = dot(ub, ww);
-    T den = a_ * c_ - b_ * b_;
-    T ta = (b_ * e_ - c_ * d_) / den, tb = (a_ * e_ - b_ * d_) / den;
+    V3<GT> ua = mcol(R1, i), ub = mcol(R2, j), ww = pa - pb;
+    GT a_ = dot(ua, ua), b_ = dot(ua, ub), c_ = dot(ub, ub), d_ = dot(ua, ww), e_ = dot(ub, ww);
+    GT den = a_ * c_ - b_ * b_;
+    GT ta = (b_ * e_ - c_ * d_) / den, tb = (a_ * e_ - b_ * d_) / den;
     ta = fmin(fmax(ta, -s1[i]), s1[i]); tb = fmin(fmax(tb, -s2[j]), s2[j]);
-    V3<T> ca = pa + ua * ta, cb = pb + ub * tb;
-    add_contact(m, w, g, ncon, nrow, pair, best, (ca + cb) * T(0.5), n);
+    V3<GT> ca = pa + ua * ta, cb = pb + ub * tb;
+    add_contact(m, w, g, ncon, nrow, pair, best, (ca + cb) * GT(0.5), n);
     return;
   }
-  const T *Rr, *sr, *Ri, *si; V3<T> pr, pi, nr; int ax;
+  const GT *Rr, *sr, *Ri, *si; V3<GT> pr, pi, nr; int ax;
   if (code < 3) { pr = p1; Rr = R1; sr = s1; pi = p2; Ri = R2; si = s2; nr = n; ax = code; }
   else { pr = p2; Rr = R2; sr = s2; pi = p1; Ri = R1; si = s1; nr = -n; ax = code - 3; }
-  V3<T> dots = multv(Ri, nr);
+  V3<GT> dots = multv(Ri, nr);
   int k = 0;
   if (fabs(dots.y) > fabs(comp(dots, k))) k = 1;
   if (fabs(dots.z) > fabs(comp(dots, k))) k = 2;
-  T sgn = comp(dots, k) > 0 ? T(-1) : T(1);
-  V3<T> fc = pi + mcol(Ri, k) * (si[k] * sgn);
+  GT sgn = comp(dots, k) > 0 ? GT(-1) : GT(1);
+  V3<GT> fc = pi + mcol(Ri, k) * (si[k] * sgn);
   int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-  V3<T> u = mcol(Ri, k1) * si[k1], v = mcol(Ri, k2) * si[k2];
-  V3<T> poly[16], tmp[16];
+  V3<GT> u = mcol(Ri, k1) * si[k1], v = mcol(Ri, k2) * si[k2];
+  V3<GT> poly[16], tmp[16];
   int np = 4;
   poly[0] = fc + u + v; poly[1] = fc - u + v; poly[2] = fc - u - v; poly[3] = fc + u - v;
   int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
   for (int side = 0; side < 4; side++) {
     int axis_id = side < 2 ? a1 : a2;
-    T sg = (side & 1) ? T(-1) : T(1);
-    V3<T> pn = mcol(Rr, axis_id) * sg;
-    T off = dot(pn, pr) + sr[axis_id];
+    GT sg = (side & 1) ? GT(-1) : GT(1);
+    V3<GT> pn = mcol(Rr, axis_id) * sg;
+    GT off = dot(pn, pr) + sr[axis_id];
     int nn = 0;
     for (int q = 0; q < np; q++) {
-      V3<T> Aq = poly[q], Bq = poly[(q + 1) % np];
-      T da = dot(pn, Aq) - off, db = dot(pn, Bq) - off;
+      V3<GT> Aq = poly[q], Bq = poly[(q + 1) % np];
+      GT da = dot(pn, Aq) - off, db = dot(pn, Bq) - off;
       if (da <= 0) tmp[nn++] = Aq;
       if ((da < 0 && db > 0) || (db < 0 && da > 0)) tmp[nn++] = Aq + (Bq - Aq) * (da / (da - db));
     }
@@ -677,12 +743,12 @@ HSR_HDN void box_box(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int&
     for (int q = 0; q < np; q++) poly[q] = tmp[q];
     if (np == 0) return;
   }
-  T face_off = dot(nr, pr) + sr[ax];
+  GT face_off = dot(nr, pr) + sr[ax];
   int cnt = 0;
   for (int q = 0; q < np && cnt < 8; q++) {
-    T dep = face_off - dot(nr, poly[q]);
+    GT dep = face_off - dot(nr, poly[q]);
     if (dep < 0) continue;
-    add_contact(m, w, g, ncon, nrow, pair, -dep, poly[q] + nr * (dep * T(0.5)), n);
+    add_contact(m, w, g, ncon, nrow, pair, -dep, poly[q] + nr * (dep * GT(0.5)), n);
     cnt++;
   }
 }
@@ -698,12 +764,11 @@ HSR_HD int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
     bool hit = false;
     if (k < m.npair) {
       int a = m.pair_geom1[k], b = m.pair_geom2[k];
-      V3<T> dp = ld3(w.gpos + 3 * b) - ld3(w.gpos + 3 * a);
+      V3<T> dp = cvt<T>(ld3(w.gpos + 3 * b) - ld3(w.gpos + 3 * a));
       if (m.geom_type[a] == GEOM_PLANE) {
-        const T* R = w.xmat + 9 * m.geom_body[a];  // plane geoms sit on the world body with identity geom_mat rows
-        T Rg[9];
-        mulm(R, m.geom_mat + 9 * a, Rg);
-        hit = dot(dp, mcol(Rg, 2)) <= m.geom_rbound[b];
+        Geom<T> P;
+        load_geom(m, w, a, P);
+        hit = dot(dp, cvt<T>(mcol(P.mat, 2))) <= m.geom_rbound[b];
       } else {
         T rr = m.geom_rbound[a] + m.geom_rbound[b];
         hit = dot(dp, dp) <= rr * rr;
@@ -724,28 +789,29 @@ HSR_HD int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
       int func = m.pair_func[pk];
       npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
       if (func == NP_PLANE_BOX) {
-        V3<T> n = mcol(A.mat, 2);
-        T dist0 = dot(B.pos - A.pos, n);
+        V3<GT> n = mcol(A.mat, 2);
+        GT dist0 = dot(B.pos - A.pos, n);
         int cnt = 0;
         for (int i = 0; i < 8 && cnt < 4; i++) {
-          V3<T> s = mk<T>((i & 1) ? B.size[0] : -B.size[0], (i & 2) ? B.size[1] : -B.size[1], (i & 4) ? B.size[2] : -B.size[2]);
-          V3<T> vec = mulv(B.mat, s);
-          T ld = dot(n, vec);
+          V3<GT> sz = mk<GT>((i & 1) ? (GT)B.size[0] : -(GT)B.size[0], (i & 2) ? (GT)B.size[1] : -(GT)B.size[1],
+                             (i & 4) ? (GT)B.size[2] : -(GT)B.size[2]);
+          V3<GT> vec = mulv(B.mat, sz);
+          GT ld = dot(n, vec);
           if (dist0 + ld > 0 || ld > 0) continue;
-          T dist = dist0 + ld;
-          add_contact(m, w, g, ncon, nrow, pk, dist, B.pos + vec - n * (dist * T(0.5)), n);
+          GT dist = dist0 + ld;
+          add_contact(m, w, g, ncon, nrow, pk, dist, B.pos + vec - n * (dist * GT(0.5)), n);
           cnt++;
         }
       } else if (func == NP_PLANE_CONVEX) {
-        V3<T> n = mcol(A.mat, 2);
-        V3<T> p = support(B, -n, g);
-        T dist = dot(p - A.pos, n);
-        if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * T(0.5)), n);
+        V3<GT> n = mcol(A.mat, 2);
+        V3<GT> p = support_d(B, -n, g);
+        GT dist = dot(p - A.pos, n);
+        if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * GT(0.5)), n);
       } else if (func == NP_BOX_BOX) {
         box_box(m, w, g, ncon, nrow, pk, A, B);
       } else {
-        T depth; V3<T> dir, pos;
-        if (mpr_penetration(A, B, m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+        GT depth; V3<GT> dir, pos;
+        if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
           add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
       }
     }
@@ -755,32 +821,34 @@ HSR_HD int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
 }
 
 // ------------------------------------------------------------------------------------------------ B.4 / B.5
-template <typename T> HSR_HD T impedance(const T* solimp, T pos) {
-  const T MINIMP = T(1e-4), MAXIMP = T(0.9999);
-  T d0 = fmin(fmax(solimp[0], MINIMP), MAXIMP), dmax = fmin(fmax(solimp[1], MINIMP), MAXIMP);
-  T width = fmax(Lim<T>::minval(), solimp[2]), mid = fmin(fmax(solimp[3], MINIMP), MAXIMP), power = fmax(T(1), solimp[4]);
-  if (d0 == dmax || width <= Lim<T>::minval()) return T(0.5) * (d0 + dmax);
-  T x = fabs(pos) / width;
+// Row parameters are evaluated in double and rounded once: R = (1 - imp)/imp * diag cancels three digits of imp.
+template <typename T> HSR_HD GT impedance(const T* solimp, GT pos) {
+  const GT MINIMP = 1e-4, MAXIMP = 0.9999;
+  GT d0 = fmin(fmax((GT)solimp[0], MINIMP), MAXIMP), dmax = fmin(fmax((GT)solimp[1], MINIMP), MAXIMP);
+  GT width = fmax(GT(1e-15), (GT)solimp[2]), mid = fmin(fmax((GT)solimp[3], MINIMP), MAXIMP), power = fmax(GT(1), (GT)solimp[4]);
+  if (d0 == dmax || width <= GT(1e-15)) return GT(0.5) * (d0 + dmax);
+  GT x = fabs(pos) / width;
   if (x >= 1) return dmax;
   if (x == 0) return d0;
-  T y;
+  GT y;
   if (power == 1) y = x;
-  else if (x <= mid) y = (T(1) / pow(mid, power - 1)) * pow(x, power);
-  else y = T(1) - (T(1) / pow(1 - mid, power - 1)) * pow(1 - x, power);
+  else if (x <= mid) y = (GT(1) / pow(mid, power - 1)) * pow(x, power);
+  else y = GT(1) - (GT(1) / pow(1 - mid, power - 1)) * pow(1 - x, power);
   return d0 + y * (dmax - d0);
 }
 
 // reference acceleration + regulariser of one scalar row
 template <typename T>
-HSR_HD void row_params(const ModelT<T>& m, const T* solref, const T* solimp, T pos, T vel, T diag, bool friction_row,
-                       T& R, T& aref) {
-  T tc = fmax(solref[0], 2 * m.timestep), dr = solref[1];
-  T dmax = fmin(fmax(solimp[1], T(1e-4)), T(0.9999));
-  T imp = impedance(solimp, pos);
-  R = fmax(Lim<T>::minval(), (1 - imp) / imp * diag);
-  T k = friction_row ? T(0) : T(1) / (dmax * dmax * tc * tc * dr * dr);
-  T b = T(2) / (dmax * tc);
-  aref = -b * vel - k * imp * pos;
+HSR_HD void row_params(const ModelT<T>& m, const T* solref, const T* solimp, T pos_, T vel, T diag, bool friction_row,
+                       GT& R, T& aref) {
+  GT pos = (GT)pos_;
+  GT tc = fmax((GT)solref[0], 2 * (GT)m.timestep), dr = (GT)solref[1];
+  GT dmax = fmin(fmax((GT)solimp[1], GT(1e-4)), GT(0.9999));
+  GT imp = impedance(solimp, pos);
+  R = fmax(GT(1e-15), (1 - imp) / imp * (GT)diag);
+  GT k = friction_row ? GT(0) : GT(1) / (dmax * dmax * tc * tc * dr * dr);
+  GT b = GT(2) / (dmax * tc);
+  aref = (T)(-b * (GT)vel - k * imp * pos);
 }
 
 // rows: active joint limits (joint order) then contacts (elliptic, dim rows each)
@@ -799,9 +867,9 @@ HSR_HD void make_constraint(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlim
         if (dist < 0) {
           T sg = side == 0 ? T(1) : T(-1);
           for (int d = 0; d < nv; d++) w.J[r * nv + d] = (d == dof) ? sg : T(0);
-          T R, aref;
+          GT R; T aref;
           row_params(m, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, sg * w.qvel[dof], m.dof_invweight0[dof], false, R, aref);
-          w.D[r] = T(1) / R; w.aref[r] = aref;
+          w.D[r] = (T)(GT(1) / R); w.aref[r] = aref;
           r++;
         }
       }
@@ -812,13 +880,14 @@ HSR_HD void make_constraint(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlim
     int pk = w.con_pair[c];
     int dim = m.pair_condim[pk], r0 = w.con_adr[c];
     uint32_t m1 = m.body_dofmask[m.geom_body[m.pair_geom1[pk]]], m2 = m.body_dofmask[m.geom_body[m.pair_geom2[pk]]];
-    V3<T> p = ld3(w.con_pos + 3 * c);
+    V3<GT> p = ldg(w.con_pos + 3 * c);
     const T* fr = w.con_frame + 9 * c;
     for (int d = g.lane; d < nv; d += Grp::G) {
       T sg = T((m2 >> d) & 1u) - T((m1 >> d) & 1u);
       const T* cd = w.cdof + 6 * d;
       V3<T> jr = ld3(cd) * sg;
-      V3<T> jp = (ld3(cd + 3) + cross(ld3(cd), p)) * sg;
+      V3<T> rel = cvt<T>(p - ld3(w.com + 3 * m.dof_body[d]));  // contact point relative to the dof's tree CoM
+      V3<T> jp = (ld3(cd + 3) + cross(ld3(cd), rel)) * sg;
       for (int r = 0; r < dim; r++)
         w.J[(r0 + r) * nv + d] = r < 3 ? dot(ld3(fr + 3 * r), jp) : dot(ld3(fr + 3 * (r - 3)), jr);
     }
@@ -830,18 +899,18 @@ HSR_HD void make_constraint(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlim
     int dim = m.pair_condim[pk], r0 = w.con_adr[c];
     const T* fri = m.pair_friction + 5 * pk;
     T diag = m.geom_invweight[m.pair_geom1[pk]] + m.geom_invweight[m.pair_geom2[pk]];
-    T R0 = 0;
+    GT R0 = 0;
     for (int r = 0; r < dim; r++) {
       T vel = 0;
       for (int d = 0; d < nv; d++) vel += w.J[(r0 + r) * nv + d] * w.qvel[d];
-      T R, aref;
+      GT R; T aref;
       row_params(m, m.pair_solref + 2 * pk, m.pair_solimp + 5 * pk, r == 0 ? w.con_dist[c] : T(0), vel, diag, r > 0, R, aref);
       if (r == 0) R0 = R;
-      else if (r == 1) R = R0 / m.impratio;
-      else R = (R0 / m.impratio) * fri[0] * fri[0] / (fri[r - 1] * fri[r - 1]);
-      w.D[r0 + r] = T(1) / R; w.aref[r0 + r] = aref;
+      else if (r == 1) R = R0 / (GT)m.impratio;
+      else R = (R0 / (GT)m.impratio) * (GT)fri[0] * (GT)fri[0] / ((GT)fri[r - 1] * (GT)fri[r - 1]);
+      w.D[r0 + r] = (T)(GT(1) / R); w.aref[r0 + r] = aref;
     }
-    w.con_mu[c] = dim > 1 ? fri[0] * sqrt((R0 / m.impratio) / R0) : fri[0];
+    w.con_mu[c] = dim > 1 ? (T)((GT)fri[0] * sqrt((R0 / (GT)m.impratio) / R0)) : fri[0];
   }
   (void)nlimit;
 }
@@ -1011,27 +1080,35 @@ HSR_HD T linesearch(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int 
     q[2] = uu; q[3] = uv; q[4] = vv; q[5] = Q0; q[6] = Q1; q[7] = Q2;
   }
   g.sync();
+  // Root of the 1-D derivative by safeguarded Newton with bracketing.  The cost is convex along the search
+  // direction, so only the derivative is consulted: comparing cost values (a difference of O(1e3) numbers that
+  // agree to 7 digits near convergence) is rounding noise in fp32 and used to end the solve one iteration early.
   T c0, d1, d2;
   ls_eval(m, w, g, nlimit, ncon, T(0), q1, q2, c0, d1, d2);
   int nev = 1;
-  T lo = 0, hi = -1, alpha = 0, bestc = c0, besta = 0;
-  for (int it = 0; it < m.ls_iterations; it++) {
-    if (fabs(d1) < gtol) break;
+  T lo = 0, hi = -1, dlo = d1, dhi = 0, alpha = 0;
+  const T rel = sqrt(Lim<T>::eps());
+  bool conv = fabs(d1) < gtol;
+  for (int it = 0; it < m.ls_iterations && !conv; it++) {
     T step = d2 > Lim<T>::minval() ? -d1 / d2 : (d1 < 0 ? T(1) : T(-1));
     T nxt = alpha + step;
     if (hi >= 0 && !(lo < nxt && nxt < hi)) nxt = T(0.5) * (lo + hi);
     if (nxt <= 0 && hi < 0) nxt = alpha * T(0.5);
     if (nxt == alpha) break;
+    bool tiny = fabs(nxt - alpha) <= rel * fabs(nxt);
     alpha = nxt;
     T c;
     ls_eval(m, w, g, nlimit, ncon, alpha, q1, q2, c, d1, d2);
     nev++;
-    if (c < bestc) { bestc = c; besta = alpha; }
-    if (d1 < 0) lo = lo > alpha ? lo : alpha;
-    else hi = (hi < 0 || alpha < hi) ? alpha : hi;
+    if (d1 < 0) { if (alpha > lo) { lo = alpha; dlo = d1; } }
+    else if (hi < 0 || alpha < hi) { hi = alpha; dhi = d1; }
+    conv = fabs(d1) < gtol || tiny;
   }
   if (g.lane == 0) w.wi[WI_LSEVAL] += nev;
-  return (bestc < c0 || fabs(d1) < gtol) ? besta : T(0);
+  if (conv) return alpha;
+  // not converged within ls_iterations: the bracket end with the smaller |derivative| (lo = 0 means no descent)
+  if (hi >= 0 && (lo <= 0 || fabs(dhi) < fabs(dlo))) return lo > 0 || fabs(dhi) < fabs(dlo) ? hi : T(0);
+  return lo;
 }
 
 // Newton solver on the primal convex cost; on exit w.qacc, w.force (and w.tmpv = J^T force) are final.
@@ -1202,13 +1279,17 @@ HSR_HD int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls,
 // mj_forward up to and including the constraint solve (sim.forward(), /root/reference/hsr/env.py:176)
 template <typename T, typename Grp>
 HSR_HD void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  HSR_PHASE_START(w, g);
   if (g.lane == 0) kinematics_lane0(m, w);
   g.sync();
+  HSR_PHASE(w, g, PH_KIN);
   cdof_geoms(m, w, g);
   g.sync();
   mass_matrix(m, w, g);
   g.sync();
+  HSR_PHASE(w, g, PH_CRB);
   if (g.lane == 0) smooth_lane0(m, w);
+  HSR_PHASE(w, g, PH_SMOOTH);
   // active joint limits (uniform count)
   int nlimit = 0;
   for (int j = 0; j < m.njnt; j++) {
@@ -1220,12 +1301,15 @@ HSR_HD void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   int nrow = nlimit;
   int ncon = collision(m, w, g, nrow);
   g.sync();
+  HSR_PHASE(w, g, PH_COLLIDE);
   make_constraint(m, w, g, nlimit, ncon);
   int it0 = w.wi[WI_ITER], ls0 = w.wi[WI_LSEVAL];
   g.sync();
   if (g.lane == 0) { w.wi[WI_NCON] = ncon; w.wi[WI_NEFC] = nrow; w.wi[WI_NLIMIT] = nlimit; }
   g.sync();
+  HSR_PHASE(w, g, PH_ROWS);
   solve_newton(m, w, g, nlimit, ncon, nrow);
+  HSR_PHASE(w, g, PH_SOLVE);
   if (g.lane == 0) {
     w.wi[WI_SUMCON] += ncon; w.wi[WI_SUMEFC] += nrow;
     w.wi[WI_KFLOP] += algorithmic_flops(m, ncon, nrow, w.wi[WI_ITER] - it0, w.wi[WI_LSEVAL] - ls0, w.wi[WI_NPFLOP]);
@@ -1239,6 +1323,7 @@ HSR_HD void substep(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   forward(m, w, g);
   if (g.lane == 0) euler_lane0(m, w);
   g.sync();
+  HSR_PHASE(w, g, PH_EULER);
 }
 
 // all(in_range(block_i, goal, geofence)) on the body positions of the last forward pass
@@ -1248,10 +1333,10 @@ HSR_HD bool goal_reached(const ModelT<T>& m, const EnvCfg<T>& cfg, const WS<T>& 
   if (!cfg.has_goal || m.nblock == 0) return false;
   bool all = true;
   for (int k = 0; k < m.nblock; k++) {
-    const T* p = w.xpos + 3 * m.block_body[k];
-    T dx = p[0] - w.mocap[0], dy = p[1] - w.mocap[1], dz = p[2] - w.mocap[2];
-    T dist = sqrt(dx * dx + dy * dy + dz * dz);
-    all = all && (dist < cfg.geofence);
+    const GT* p = w.xpos + 3 * m.block_body[k];
+    GT dx = p[0] - (GT)w.mocap[0], dy = p[1] - (GT)w.mocap[1], dz = p[2] - (GT)w.mocap[2];
+    GT dist = sqrt(dx * dx + dy * dy + dz * dz);
+    all = all && (dist < (GT)cfg.geofence);
   }
   return all;
 }

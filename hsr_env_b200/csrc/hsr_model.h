@@ -100,6 +100,7 @@ struct ModelT {
   int iterations, ls_iterations, mpr_iterations;
   int any_damping;
   uint32_t body_dofmask[HSRB_MAXBODY];  // dofs that move each body (ancestors' dofs included)
+  int body_root[HSRB_MAXBODY];          // the ancestor attached to the world (root of the body's kinematic tree)
 #define X(name, isf, cnt) const typename std::conditional<isf, T, int>::type* name;
   HSRB_FIELDS(X)
 #undef X
@@ -157,6 +158,9 @@ struct HostModel {
         c = m.body_parent[c];
       }
       m.body_dofmask[b] = mask;
+      int r = b;
+      while (r > 0 && m.body_parent[r] > 0) r = m.body_parent[r];
+      m.body_root[b] = r;
     }
     // default capacities: 4 plane contacts per block, up to 8 box-box per block pair / block-pan, a few hull contacts
     m.ncon_max = 8 + 4 * m.nblock + (m.nblock > 1 ? 4 * m.nblock : 0);

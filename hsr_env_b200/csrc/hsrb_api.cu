@@ -359,6 +359,7 @@ int hsrb_debug_substep(hsrb_t* h, const float* ctrl, double* dump, void* stream)
 }
 
 int hsrb_stats(hsrb_t* h, int64_t* out9, void* stream) {
+  static_assert(ST_COUNT == 16, "hsrb.h documents 16 counters");
   if (!h || !out9) return fail(-1, "bad arguments");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize((cudaStream_t)stream));

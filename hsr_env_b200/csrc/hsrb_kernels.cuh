@@ -13,7 +13,7 @@
 
 using namespace hsr;
 
-enum { ST_SUBSTEPS = 0, ST_ITERS, ST_NARROW, ST_LSEVAL, ST_CONTACTS, ST_ROWS, ST_LAUNCHES, ST_BAD, ST_FLOPS, ST_COUNT };
+enum { ST_SUBSTEPS = 0, ST_ITERS, ST_NARROW, ST_LSEVAL, ST_CONTACTS, ST_ROWS, ST_LAUNCHES, ST_BAD, ST_FLOPS, ST_PHASE0, ST_COUNT = ST_PHASE0 + PH_COUNT };
 
 struct KArgs {
   ModelT<float> m;
@@ -90,16 +90,16 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
       if (g.lane == 0) kinematics_lane0(a.m, w);
       g.sync();
       if (a.body_xpos)
-        for (int i = g.lane; i < a.m.nbody * 3; i += G) a.body_xpos[(size_t)env * a.m.nbody * 3 + i] = w.xpos[i];
+        for (int i = g.lane; i < a.m.nbody * 3; i += G) a.body_xpos[(size_t)env * a.m.nbody * 3 + i] = (float)w.xpos[i];
       if (a.gripper && g.lane < 3) {
-        float s = 0.f;
+        GT s = 0;
         for (int k = 0; k < 2; k++) {
           int b = a.m.finger_body[k];
-          const float* R = w.xmat + 9 * b;
+          const GT* R = w.xmat + 9 * b;
           const float* p = a.m.finger_pos + 3 * k;
-          s += w.xpos[3 * b + g.lane] + R[3 * g.lane] * p[0] + R[3 * g.lane + 1] * p[1] + R[3 * g.lane + 2] * p[2];
+          s += w.xpos[3 * b + g.lane] + R[3 * g.lane] * (GT)p[0] + R[3 * g.lane + 1] * (GT)p[1] + R[3 * g.lane + 2] * (GT)p[2];
         }
-        a.gripper[(size_t)env * 3 + g.lane] = 0.5f * s;
+        a.gripper[(size_t)env * 3 + g.lane] = (float)(0.5 * s);
       }
       success = goal_reached(a.m, a.cfg, w);
     }
@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
       atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)w.wi[WI_SUMCON]);
       atomicAdd(a.stats + ST_ROWS, (unsigned long long)w.wi[WI_SUMEFC]);
       atomicAdd(a.stats + ST_FLOPS, (unsigned long long)w.wi[WI_KFLOP]);
+#ifdef HSRB_PHASE_CLOCKS
+      for (int k = 0; k < PH_COUNT; k++) atomicAdd(a.stats + ST_PHASE0 + k, (unsigned long long)w.wi[WI_PHASE0 + k]);
+#endif
       if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
       }
     }

@@ -306,11 +306,14 @@ class BatchedHSREnv:
         return dump
 
     def stats(self) -> dict:
-        v = (ctypes.c_int64 * 9)()
+        v = (ctypes.c_int64 * 16)()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_stats(self._h, v, self._stream()))
         keys = ["substeps", "newton_iters", "narrowphase", "ls_evals", "contacts", "efc_rows", "launches", "bad_envs", "flops"]
-        return dict(zip(keys, [int(x) for x in v]))
+        out = dict(zip(keys, [int(x) for x in v]))
+        phases = ["kinematics", "mass_matrix", "smooth", "collision", "rows", "solver", "euler"]
+        out["phase_cycles"] = {k: int(v[9 + i]) * 16 for i, k in enumerate(phases)}
+        return out
 
     def launch_info(self) -> dict:
         v = (ctypes.c_int * 4)()

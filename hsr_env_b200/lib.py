@@ -10,7 +10,9 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libhsrb.so"
+import os
+
+LIB_PATH = Path(os.environ.get("HSRB_LIB", CSRC / "libhsrb.so"))  # HSRB_LIB: e.g. the phase-clock build
 
 # every symbol include/hsrb.h declares: (restype, argtypes)
 SIGNATURES = {

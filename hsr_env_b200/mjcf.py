@@ -737,6 +737,12 @@ def compile_model(xml_path: Path, use_dof: Sequence[str], n_blocks: int = 0,
     arr.update(block_body=A(block_body, np.int32, (len(block_body),)), finger_body=finger_body,
                finger_pos=finger_pos, mocap_pos0=A(mocap[0] if mocap else [0, 0, 0], float, (3,)))
 
+    # Every float constant of the blob is rounded to an fp32-representable value (MuJoCo itself stores mesh
+    # vertices as float): the CUDA path (fp32 model, double geometry stage) and the fp64 oracle then see identical
+    # constants, so that one-step parity measures arithmetic, not a 1e-8 difference in the geometry.
+    for k_, v_ in list(arr.items()):
+        if v_.dtype == np.float64:
+            arr[k_] = v_.astype(np.float32).astype(np.float64)
     mdl = M.Model(nq=nq, nv=nv, nu=nu, nbody=nbody, njnt=njnt, ngeom=ngeom, nvert=len(hull_vert), npair=npair,
                   nblock=len(block_body), arrays=arr)
     mdl.names = dict(body=[bodies[i].name for i in fused_ids], joint=jnt_names,

@@ -79,8 +79,10 @@ int hsrb_debug_substep(hsrb_t* h, const float* ctrl, double* dump, void* stream)
 /* Cumulative counters since creation, copied to host (synchronises `stream`):
  * [0] substeps executed, [1] Newton iterations, [2] narrowphase calls, [3] line-search evaluations,
  * [4] contacts (summed over substeps), [5] constraint rows (summed), [6] kernel launches, [7] environments
- * flagged bad, [8] algorithmic flops (SURVEY.md §8(d) stage formulas with the actual per-substep counts). */
-int hsrb_stats(hsrb_t* h, int64_t* out9_host, void* stream);
+ * flagged bad, [8] algorithmic flops (SURVEY.md §8(d) stage formulas with the actual per-substep counts),
+ * [9..15] lane-0 clock64 cycles / 16 per phase (kinematics, mass matrix, smooth forces, collision, constraint
+ * rows, solver, integration) - zero unless the library was built with -DHSRB_PHASE_CLOCKS. */
+int hsrb_stats(hsrb_t* h, int64_t* out16_host, void* stream);
 
 /* Introspection used by bench.py: lanes per env, shared-memory bytes per env, resident envs per SM, grid. */
 int hsrb_launch_info(hsrb_t* h, int* out4_host);
