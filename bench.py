@@ -183,7 +183,7 @@ def run_gpu(args):
     n = args.envs_per_gpu
     goals = [GoalSpec(a=Box(BLOCK_LO, BLOCK_HI), b=Box(GOAL_LO, GOAL_HI), distance=GEOFENCE)]
     env = BatchedHSREnv(BLOB, goals, steps_per_action=NSUB, n_envs=n, device=dev, seed=args.seed,
-                        env_id_offset=rank * n, lanes_per_env=args.lanes)
+                        env_id_offset=rank * n, lanes_per_env=args.lanes, kernel=args.kernel)
     info = env.launch_info()
     lo = torch.tensor(env.model.act_ctrlrange[:, 0], dtype=torch.float32, device=dev)
     hi = torch.tensor(env.model.act_ctrlrange[:, 1], dtype=torch.float32, device=dev)
@@ -269,7 +269,7 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * secs_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": n * world, "substeps_per_action": NSUB,
-                   "l2": "flushed (256 MiB write) between timed steps", "lanes_per_env": info["lanes_per_env"],
+                   "l2": "flushed (256 MiB write) between timed steps", "kernel": info["kernel"], "threads_per_block": info["threads_per_block"], "lanes_per_env": info["lanes_per_env"],
                    "smem_per_env": info["smem_per_env"], "resident_envs_per_sm": info["envs_per_sm"], "grid": info["grid"]},
         "substeps_per_s": sub_total / secs_max, "mean_substeps_per_action": sub_total / (world * n * args.steps),
         "success_per_action": succ_total / (world * n * args.steps), "bad_states": bad_total,
@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = auto)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

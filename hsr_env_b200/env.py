@@ -85,6 +85,7 @@ class BatchedHSREnv:
             min_block_separation: float = 0.0,
             block_quat_index: Sequence[int] = (0, 2),
             lanes_per_env: int = 0,
+            kernel: str = "auto",
     ):
         if any([render, record, render_freq, record_freq, record_path]):
             raise NotImplementedError("render/record need an OpenGL viewer and are outside the batched backend "
@@ -111,6 +112,8 @@ class BatchedHSREnv:
                                          ctypes.byref(self._h)))
         if lanes_per_env:
             _lib.check(self._lib.hsrb_config(self._h, int(lanes_per_env), 0, 0))
+        # "auto": register-resident fast kernel for the sliding-base + <=1 block family, else the general kernel
+        self.kernel_path = _lib.check(self._lib.hsrb_set_path(self._h, {"auto": 0, "general": 1, "fast": 2}[kernel]))
         m = self.model
         self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
         self.obs_dim = self.nq + self.nv
@@ -316,10 +319,11 @@ class BatchedHSREnv:
         return out
 
     def launch_info(self) -> dict:
-        v = (ctypes.c_int * 4)()
+        v = (ctypes.c_int * 6)()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_launch_info(self._h, v))
-        return dict(lanes_per_env=v[0], smem_per_env=v[1], envs_per_sm=v[2], grid=v[3])
+        return dict(lanes_per_env=v[0], smem_per_env=v[1], envs_per_sm=v[2], grid=v[3],
+                    kernel={1: "general", 2: "fast"}.get(v[4], "?"), threads_per_block=v[5])
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -20,6 +20,7 @@ SIGNATURES = {
     "hsrb_destroy": (c_int, [c_void_p]),
     "hsrb_dims": (c_int, [c_void_p] + [POINTER(c_int)] * 5),
     "hsrb_config": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "hsrb_set_path": (c_int, [c_void_p, c_int]),
     "hsrb_set_goals": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), c_float, c_float, c_int, c_int]),
     "hsrb_reset": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsrb_step": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 7),

@@ -34,6 +34,11 @@ int hsrb_dims(hsrb_t* h, int* nq, int* nv, int* nu, int* nbody, int* nblock);
  * /root/reference/hsr/models/world.xml:44). */
 int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max);
 
+/* Kernel selection: 0 = auto (the register-resident fast kernel when the model is a sliding base with at most
+ * one free box - the README block-push family - else the general kernel), 1 = general kernel, 2 = fast kernel
+ * (error if the model is outside that family).  Returns the path that will run (1 or 2). */
+int hsrb_set_path(hsrb_t* h, int path);
+
 /* GoalSpec(a=block_space, b=goal_space, distance=geofence)  /root/reference/hsr/util.py:70-74, env.py:161-172
  * goal_lohi = {lo[3], hi[3]} (NULL: goals=None, the env is never done), block_lohi = {lo[4], hi[4]} over
  * (x, y, quat[qidx0], quat[qidx1]); min_sep > 0 rejection-samples block (x,y) at least that far apart. */
@@ -84,8 +89,9 @@ int hsrb_debug_substep(hsrb_t* h, const float* ctrl, double* dump, void* stream)
  * rows, solver, integration) - zero unless the library was built with -DHSRB_PHASE_CLOCKS. */
 int hsrb_stats(hsrb_t* h, int64_t* out16_host, void* stream);
 
-/* Introspection used by bench.py: lanes per env, shared-memory bytes per env, resident envs per SM, grid. */
-int hsrb_launch_info(hsrb_t* h, int* out4_host);
+/* Introspection used by bench.py: lanes per env, shared-memory bytes per env, resident envs per SM, grid,
+ * path (1 general, 2 fast), threads per block. */
+int hsrb_launch_info(hsrb_t* h, int* out6_host);
 
 const char* hsrb_last_error(void);
 
