@@ -753,6 +753,42 @@ HSR_HDN void box_box(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int&
   }
 }
 
+// Narrowphase of one candidate pair that passed the culls (mjc_PlaneBox / plane-convex / box-box / mjc_Convex).
+template <typename T, typename Grp>
+HSR_HD void narrow_pair(const ModelT<T>& m, WS<T>& w, const Grp& g, int pk, int& ncon, int& nrow, int& npflop) {
+  Geom<T> A, B;
+  load_geom(m, w, m.pair_geom1[pk], A);
+  load_geom(m, w, m.pair_geom2[pk], B);
+  int func = m.pair_func[pk];
+  npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
+  if (func == NP_PLANE_BOX) {
+    V3<GT> n = mcol(A.mat, 2);
+    GT dist0 = dot(B.pos - A.pos, n);
+    int cnt = 0;
+    for (int i = 0; i < 8 && cnt < 4; i++) {
+      V3<GT> sz = mk<GT>((i & 1) ? (GT)B.size[0] : -(GT)B.size[0], (i & 2) ? (GT)B.size[1] : -(GT)B.size[1],
+                         (i & 4) ? (GT)B.size[2] : -(GT)B.size[2]);
+      V3<GT> vec = mulv(B.mat, sz);
+      GT ld = dot(n, vec);
+      if (dist0 + ld > 0 || ld > 0) continue;
+      GT dist = dist0 + ld;
+      add_contact(m, w, g, ncon, nrow, pk, dist, B.pos + vec - n * (dist * GT(0.5)), n);
+      cnt++;
+    }
+  } else if (func == NP_PLANE_CONVEX) {
+    V3<GT> n = mcol(A.mat, 2);
+    V3<GT> p = support_d(B, -n, g);
+    GT dist = dot(p - A.pos, n);
+    if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * GT(0.5)), n);
+  } else if (func == NP_BOX_BOX) {
+    box_box(m, w, g, ncon, nrow, pk, A, B);
+  } else {
+    GT depth; V3<GT> dir, pos;
+    if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+      add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
+  }
+}
+
 // Candidate pairs -> bounding sphere + conservative world-AABB cull -> narrowphase.  Returns #contacts;
 // nrow is advanced by the constraint rows the contacts will occupy.
 template <typename T, typename Grp>
@@ -781,39 +817,8 @@ HSR_HD int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
       int l = 0;
       while (!((bits >> l) & 1u)) l++;
       bits &= bits - 1;
-      int pk = base + l;
       narrow++;
-      Geom<T> A, B;
-      load_geom(m, w, m.pair_geom1[pk], A);
-      load_geom(m, w, m.pair_geom2[pk], B);
-      int func = m.pair_func[pk];
-      npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
-      if (func == NP_PLANE_BOX) {
-        V3<GT> n = mcol(A.mat, 2);
-        GT dist0 = dot(B.pos - A.pos, n);
-        int cnt = 0;
-        for (int i = 0; i < 8 && cnt < 4; i++) {
-          V3<GT> sz = mk<GT>((i & 1) ? (GT)B.size[0] : -(GT)B.size[0], (i & 2) ? (GT)B.size[1] : -(GT)B.size[1],
-                             (i & 4) ? (GT)B.size[2] : -(GT)B.size[2]);
-          V3<GT> vec = mulv(B.mat, sz);
-          GT ld = dot(n, vec);
-          if (dist0 + ld > 0 || ld > 0) continue;
-          GT dist = dist0 + ld;
-          add_contact(m, w, g, ncon, nrow, pk, dist, B.pos + vec - n * (dist * GT(0.5)), n);
-          cnt++;
-        }
-      } else if (func == NP_PLANE_CONVEX) {
-        V3<GT> n = mcol(A.mat, 2);
-        V3<GT> p = support_d(B, -n, g);
-        GT dist = dot(p - A.pos, n);
-        if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * GT(0.5)), n);
-      } else if (func == NP_BOX_BOX) {
-        box_box(m, w, g, ncon, nrow, pk, A, B);
-      } else {
-        GT depth; V3<GT> dir, pos;
-        if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
-          add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
-      }
+      narrow_pair(m, w, g, base + l, ncon, nrow, npflop);
     }
   }
   if (g.lane == 0) { w.wi[WI_NARROW] += narrow; w.wi[WI_NPFLOP] = npflop; }

@@ -113,14 +113,17 @@ __global__ void __launch_bounds__(256) hsrb_fast_kernel(const __grid_constant__ 
         w.qpos[i] = v;
       }
       g.sync();
+      HSR_PHASE_START(w, g);
       if (g.lane == 0) kinematics_lane0(m, w);
       g.sync();
+      HSR_PHASE(w, g, PH_KIN);
       if (HASB) {
 #pragma unroll
         for (int k = 5; k < 9; k++) qpos[k] = w.qpos[k];  // quaternion normalised in place
       }
       cdof_geoms(m, w, g);
       g.sync();
+      HSR_PHASE(w, g, PH_CRB);
       // active joint limits (redundant in every lane)
       float lim_sg[2], lim_D[2], lim_aref[2];
       int nlimit = 0;
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(256) hsrb_fast_kernel(const __grid_constant__ 
       g.sync();
       if (ncon > HSRB_FAST_MAXCON) { ncon = HSRB_FAST_MAXCON; }
       flags |= w.wi[WI_FLAGS];
+      HSR_PHASE(w, g, PH_COLLIDE);
 
       // ---------------------------------------------------------------- smooth forces (closed form, B.6)
       float qs[8], as[8];  // qfrc_smooth, qacc_smooth
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(256) hsrb_fast_kernel(const __grid_constant__ 
       }
       const int nefc = nrow;
       sumcon += ncon; sumefc += nefc;
+      HSR_PHASE(w, g, PH_ROWS);
 
       // ---------------------------------------------------------------- Newton solver (B.7), registers only
       float x[8], Ma[8], qfc[8];  // qacc, M qacc, J^T f
@@ -584,6 +589,7 @@ __global__ void __launch_bounds__(256) hsrb_fast_kernel(const __grid_constant__ 
           }
         }
       }
+      HSR_PHASE(w, g, PH_SOLVE);
       n_iter += it; n_ls += ls_used;
       kflop += algorithmic_flops(m, ncon, nefc, it, ls_used, w.wi[WI_NPFLOP]);
 
@@ -618,6 +624,7 @@ __global__ void __launch_bounds__(256) hsrb_fast_kernel(const __grid_constant__ 
       }
       taken++;
       g.sync();
+      HSR_PHASE(w, g, PH_EULER);
       if (reached) { success = true; break; }
     }
 
@@ -648,6 +655,9 @@ __global__ void __launch_bounds__(256) hsrb_fast_kernel(const __grid_constant__ 
         atomicAdd(a.stats + ST_ROWS, (unsigned long long)sumefc);
         atomicAdd(a.stats + ST_FLOPS, (unsigned long long)kflop);
         if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
+#ifdef HSRB_PHASE_CLOCKS
+        for (int k = 0; k < PH_COUNT; k++) atomicAdd(a.stats + ST_PHASE0 + k, (unsigned long long)w.wi[WI_PHASE0 + k]);
+#endif
       }
     }
     g.sync();

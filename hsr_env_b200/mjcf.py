@@ -85,6 +85,7 @@ class CompileOptions:
     """Version-dependent compile choices."""
     mesh_inertia: str = "legacy"  # legacy | exact | convex   (App. A.5)
     solimp_params: int = 5  # 5-parameter impedance (MuJoCo >= 2.0); 3 pads to a linear ramp
+    prune_static_pairs: bool = True  # drop candidate pairs that joint ranges make unreachable (same contacts, less work)
     block_quat_index: Tuple[int, int] = (0, 2)  # which free-joint quaternion comps block-space drives
     # (hsr/__init__.py:15-17 varies q1 and q3 of [x y z q1 q2 q3 q4]  ->  indices 0 and 2)
 
@@ -683,6 +684,7 @@ def compile_model(xml_path: Path, use_dof: Sequence[str], n_blocks: int = 0,
             i1, i2 = name_to_id[b1], name_to_id[b2]
             excl.add((min(i1, i2), max(i1, i2)))
     weldparent = {i: (bodies[bodies[b.weld].parent].weld if b.weld else 0) for i, b in enumerate(bodies)}
+    mdl_info_prune = {}
     pairs = []
     for a in range(ngeom):
         for c in range(a + 1, ngeom):
@@ -715,6 +717,9 @@ def compile_model(xml_path: Path, use_dof: Sequence[str], n_blocks: int = 0,
                               friction=[fr[0], fr[0], fr[1], fr[2], fr[2]],
                               solref=mix * x.solref + (1 - mix) * y.solref,
                               solimp=mix * x.solimp + (1 - mix) * y.solimp))
+    if opts.prune_static_pairs:
+        pairs = _prune_unreachable_pairs(pairs, arr, kin, nbody, geom_body, geom_type, geom_pos, geom_mat, geom_size,
+                                         vertadr, vertnum, hull_vert, mesh_info=mdl_info_prune)
     npair = len(pairs)
     arr.update(
         pair_geom1=A([p["g1"] for p in pairs], np.int32, (npair,)),
@@ -752,6 +757,75 @@ def compile_model(xml_path: Path, use_dof: Sequence[str], n_blocks: int = 0,
                     total_geoms=sum(len(b.geoms) for b in bodies), mesh_inertia=opts.mesh_inertia)
     mdl.validate()
     return mdl
+
+
+# ----------------------------------------------------------------------------- static pair pruning
+def _prune_unreachable_pairs(pairs, arr, kin, nbody, geom_body, geom_type, geom_pos, geom_mat, geom_size, vertadr,
+                             vertnum, hull_vert, mesh_info, slack=0.05):
+    """Drop candidate pairs between a static (world) geom and a geom whose body can only translate along limited
+    slide joints, when the volume swept over the joint ranges (+ ``slack`` metres beyond each soft limit) cannot
+    reach the static geom.  Purely a work reduction: a pruned pair could never produce a contact."""
+    njnt = len(arr["jnt_type"])
+
+    def slide_only_chain(f):
+        """list of (axis_world, lo - q0, hi - q0) of the joints between body f and the world, or None."""
+        out = []
+        b = f
+        while b > 0:
+            for j in range(arr["body_jntadr"][b], arr["body_jntadr"][b] + arr["body_jntnum"][b]):
+                if arr["jnt_type"][j] != M.JNT_SLIDE or not arr["jnt_limited"][j]:
+                    return None
+                q0 = arr["qpos0"][arr["jnt_qposadr"][j]]
+                out.append((kin["axis"][j], arr["jnt_range"][j, 0] - q0 - slack, arr["jnt_range"][j, 1] - q0 + slack))
+            b = arr["body_parent"][b]
+        return out
+
+    def local_points(g):
+        t = geom_type[g]
+        if t == M.GEOM_MESH:
+            return hull_vert[vertadr[g]:vertadr[g] + vertnum[g]]
+        s = geom_size[g]
+        if t == M.GEOM_BOX:
+            return np.array([[sx * s[0], sy * s[1], sz * s[2]] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+        if t == M.GEOM_CYLINDER:  # conservative: bounding box of the cylinder
+            return np.array([[sx * s[0], sy * s[0], sz * s[1]] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+        return None
+
+    def world_points(g):
+        f = geom_body[g]
+        R = kin["xmat"][f] @ geom_mat[g].reshape(3, 3)
+        c = kin["xpos"][f] + kin["xmat"][f] @ geom_pos[g]
+        pts = local_points(g)
+        return None if pts is None else c + pts @ R.T
+
+    kept = []
+    for p in pairs:
+        a, b = p["g1"], p["g2"]
+        fa, fb = geom_body[a], geom_body[b]
+        if (fa == 0) == (fb == 0):
+            kept.append(p); continue
+        st, mv = (a, b) if fa == 0 else (b, a)
+        chain = slide_only_chain(geom_body[mv])
+        pts = world_points(mv)
+        if chain is None or pts is None:
+            kept.append(p); continue
+        lo, hi = pts.min(0).copy(), pts.max(0).copy()
+        for ax, dlo, dhi in chain:
+            lo += np.minimum(ax * dlo, ax * dhi); hi += np.maximum(ax * dlo, ax * dhi)
+        if geom_type[st] == M.GEOM_PLANE:
+            Rs = kin["xmat"][0] @ geom_mat[st].reshape(3, 3)
+            n = Rs[:, 2]; p0 = geom_pos[st]
+            corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+            reachable = ((corners - p0) @ n).min() <= 1e-6
+        else:
+            spts = world_points(st)
+            if spts is None:
+                kept.append(p); continue
+            slo, shi = spts.min(0), spts.max(0)
+            reachable = bool(np.all(lo <= shi + 1e-6) and np.all(slo <= hi + 1e-6))
+        if reachable:
+            kept.append(p)
+    return kept
 
 
 # ----------------------------------------------------------------------------- compile-time kinematics

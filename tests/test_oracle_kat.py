@@ -70,20 +70,22 @@ def test_kat3_resting_block_carries_its_weight(models):
 
 
 def test_kat4_joint_limit_holds(models):
-    """Base driven into its upper slide_x limit: the limit row activates and stops it within a millimetre."""
+    """Base driven into its lower slide_x limit (the upper one is out of reach: the pan edge stops the base first,
+    SURVEY.md App. A.6): the limit row activates and stops it within a millimetre."""
     m = models["c1_readme"]
     d = fresh(m)
-    d.qpos[:] = [0.215, 0.0]; d.ctrl[:] = [1.0, 0.0]
+    d.qpos[:] = [-0.115, 0.0]; d.ctrl[:] = [-1.0, 0.0]
     active = 0
     for _ in range(1500):
         mjstep.step(m, d)
         active += d.nlimit
-    hi = m.jnt_range[0, 1]
+    lo = m.jnt_range[0, 0]
     assert active > 0
-    assert hi < d.qpos[0] < hi + 2e-3
+    assert len(d.contacts) == 0
+    assert lo - 2e-3 < d.qpos[0] < lo
     assert abs(d.qvel[0]) < 1e-6
     # steady state: constraint force balances the saturated actuator (gear * forcemax)
-    assert d.qfrc_constraint[0] == pytest.approx(-m.act_gear[0] * m.act_forcerange[0, 1], rel=1e-6)
+    assert d.qfrc_constraint[0] == pytest.approx(m.act_gear[0] * m.act_forcerange[0, 1], rel=1e-6)
 
 
 def test_kat5_mirror_symmetry(models):
