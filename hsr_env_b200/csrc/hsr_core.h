@@ -16,10 +16,19 @@
 
 #include "hsr_model.h"
 
+// HSR_HDN: out-of-line on the device (one copy of the big routines), HSR_HDC: out-of-line only in translation units
+// that define HSR_COMPACT (the register-resident kernels, whose own code is large; measured +10 % there, -20 % in
+// the shared-memory kernel, where the extra calls spill the workspace pointer table).
 #if defined(__CUDACC__)
 #define HSR_HD __host__ __device__ __forceinline__
 #define HSR_HDN __host__ __device__ __noinline__
+#if defined(HSR_COMPACT)
+#define HSR_HDC __host__ __device__ __noinline__
 #else
+#define HSR_HDC __host__ __device__ __forceinline__
+#endif
+#else
+#define HSR_HDC inline
 #define HSR_HD inline
 #define HSR_HDN inline
 #endif
@@ -216,7 +225,7 @@ template <typename T> HSR_HD void inert_mul(const T* I, const T* v, T* f) {  // 
 }
 
 template <typename T>
-HSR_HD void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
+HSR_HDC void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
   // world
   for (int k = 0; k < 3; k++) { w.xpos[k] = 0; w.xipos[k] = 0; }
   for (int k = 0; k < 9; k++) w.xmat[k] = (k % 4 == 0) ? GT(1) : GT(0);
@@ -307,7 +316,7 @@ HSR_HD void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
 
 // B.2 (part): motion axes about the tree CoM, [ang; lin]; geom centres + world AABB half extents
 template <typename T, typename Grp>
-HSR_HD void cdof_geoms(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+HSR_HDC void cdof_geoms(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   for (int j = g.lane; j < m.njnt; j += Grp::G) {
     int a = m.jnt_dofadr[j], b = m.jnt_body[j], t = m.jnt_type[j];
     if (t == JNT_FREE) {
@@ -344,7 +353,7 @@ HSR_HD void cdof_geoms(const ModelT<T>& m, WS<T>& w, const Grp& g) {
 
 // B.2: dense joint-space inertia by the composite-rigid-body method; one dof row per lane
 template <typename T, typename Grp>
-HSR_HD void mass_matrix(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+HSR_HDC void mass_matrix(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   int nv = m.nv;
   for (int i = g.lane; i < nv; i += Grp::G) {
     T f[6];
@@ -365,7 +374,7 @@ HSR_HD void mass_matrix(const ModelT<T>& m, WS<T>& w, const Grp& g) {
 }
 
 // dense Cholesky A = L L^T (lower, in place) and solves; serial (lane 0)
-template <typename T> HSR_HD bool chol_factor(T* A, int n) {
+template <typename T> HSR_HDC bool chol_factor(T* A, int n) {
   bool ok = true;
   for (int k = 0; k < n; k++) {
     T d = A[k * n + k];
@@ -382,7 +391,7 @@ template <typename T> HSR_HD bool chol_factor(T* A, int n) {
   }
   return ok;
 }
-template <typename T> HSR_HD void chol_solve(const T* L, int n, T* x) {
+template <typename T> HSR_HDC void chol_solve(const T* L, int n, T* x) {
   for (int i = 0; i < n; i++) {
     T s = x[i];
     for (int j = 0; j < i; j++) s -= L[i * n + j] * x[j];
@@ -407,7 +416,7 @@ template <typename T> HSR_HD void cross_force(const T* v, const T* f, T* r) {
 
 // lane 0: RNE bias, passive, actuation -> qfrc_smooth; factor M -> L; qacc_smooth
 template <typename T>
-HSR_HD void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
+HSR_HDC void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
   int nv = m.nv;
   T cvel[HSRB_MAXBODY][6], cacc[HSRB_MAXBODY][6], cfrc[HSRB_MAXBODY][6];
   for (int k = 0; k < 6; k++) { cvel[0][k] = 0; cacc[0][k] = 0; cfrc[0][k] = 0; }
@@ -484,7 +493,7 @@ template <typename T> HSR_HD void make_frame(V3<GT> n, T* fr) {
 }
 
 template <typename T, typename Grp>
-HSR_HD void add_contact(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, GT dist, V3<GT> pos,
+HSR_HDC void add_contact(const ModelT<T>& m, WS<T>& w, const Grp& g, int& ncon, int& nrow, int pair, GT dist, V3<GT> pos,
                         V3<GT> n) {
   int dim = m.pair_condim[pair];
   if (ncon >= m.ncon_max || nrow + dim > m.nefc_max) {
@@ -535,7 +544,7 @@ template <typename T> HSR_HD T origin_tri_dist2(V3<T> a, V3<T> b, V3<T> c, V3<T>
 // thresholds, which fp32 cannot resolve (a 0.1 mm contact came out with a different face normal).  Only the
 // vertex scan of a hull (the bulk of the work) runs in T; its result is an index, i.e. exact.
 template <typename T, typename Grp>
-HSR_HD V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
+HSR_HDC V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
   typedef double W;
   const W* R = ge.mat;
   V3<W> dl = multv(R, d), res;
@@ -559,12 +568,18 @@ HSR_HD V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
   return ge.pos + mulv(R, res);
 }
 
+// support point of the Minkowski difference g1 - g2 along d (one out-of-line copy: it is called from ~6 sites)
+template <typename T, typename Grp>
+HSR_HDC void mpr_support(const Geom<T>& g1, const Geom<T>& g2, V3<double> d, const Grp& g, Sup<double>& s) {
+  s.v1 = support_d(g1, d, g); s.v2 = support_d(g2, -d, g); s.v = s.v1 - s.v2;
+}
+
 // Minkowski Portal Refinement penetration query (libccd ccdMPRPenetration as used by mjc_Convex).
 template <typename T, typename Grp>
 HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,
                              V3<GT>& pdir_, V3<GT>& ppos_) {
   typedef double W;
-  auto sup = [&](V3<W> d) { Sup<W> s; s.v1 = support_d(g1, d, g); s.v2 = support_d(g2, -d, g); s.v = s.v1 - s.v2; return s; };
+  auto sup = [&](V3<W> d) { Sup<W> s; mpr_support(g1, g2, d, g, s); return s; };
   auto reach_tol = [&](const Sup<W>& v1, const Sup<W>& v2, const Sup<W>& v3, const Sup<W>& v4, V3<W> d) {
     W dv4 = dot(v4.v, d);
     W d1 = dv4 - dot(v1.v, d), d2 = dv4 - dot(v2.v, d), d3 = dv4 - dot(v3.v, d);
@@ -792,7 +807,7 @@ HSR_HD void narrow_pair(const ModelT<T>& m, WS<T>& w, const Grp& g, int pk, int&
 // Candidate pairs -> bounding sphere + conservative world-AABB cull -> narrowphase.  Returns #contacts;
 // nrow is advanced by the constraint rows the contacts will occupy.
 template <typename T, typename Grp>
-HSR_HD int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
+HSR_HDC int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
   int ncon = 0;
   int narrow = 0, npflop = 0;
   for (int base = 0; base < m.npair; base += Grp::G) {
@@ -844,7 +859,7 @@ template <typename T> HSR_HD GT impedance(const T* solimp, GT pos) {
 
 // reference acceleration + regulariser of one scalar row
 template <typename T>
-HSR_HD void row_params(const ModelT<T>& m, const T* solref, const T* solimp, T pos_, T vel, T diag, bool friction_row,
+HSR_HDC void row_params(const ModelT<T>& m, const T* solref, const T* solimp, T pos_, T vel, T diag, bool friction_row,
                        GT& R, T& aref) {
   GT pos = (GT)pos_;
   GT tc = fmax((GT)solref[0], 2 * (GT)m.timestep), dr = (GT)solref[1];
@@ -858,7 +873,7 @@ HSR_HD void row_params(const ModelT<T>& m, const T* solref, const T* solimp, T p
 
 // rows: active joint limits (joint order) then contacts (elliptic, dim rows each)
 template <typename T, typename Grp>
-HSR_HD void make_constraint(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon) {
+HSR_HDC void make_constraint(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon) {
   int nv = m.nv;
   // limit rows (recomputed by every lane; lane 0 writes)
   if (g.lane == 0) {
@@ -935,7 +950,7 @@ HSR_HD int cone_zone(const T* x, int dim, T mu, const T* fri, T& N, T& Tn) {
 
 // constraint cost of the current w.jar (rows across lanes / one contact per lane); optionally force + W rows
 template <typename T, typename Grp>
-HSR_HD T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, bool full) {
+HSR_HDC T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, bool full) {
   int nv = m.nv;
   T cost = 0;
   for (int i = g.lane; i < nlimit; i += Grp::G) {
@@ -1004,7 +1019,7 @@ HSR_HD T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimi
 
 // jar = J x - aref (rows across lanes), Ma = M x (dofs across lanes); returns the Gauss term
 template <typename T, typename Grp>
-HSR_HD T residuals(const ModelT<T>& m, WS<T>& w, const Grp& g, const T* x, int nefc) {
+HSR_HDC T residuals(const ModelT<T>& m, WS<T>& w, const Grp& g, const T* x, int nefc) {
   int nv = m.nv;
   for (int r = g.lane; r < nefc; r += Grp::G) {
     T s = -w.aref[r];
@@ -1022,7 +1037,7 @@ HSR_HD T residuals(const ModelT<T>& m, WS<T>& w, const Grp& g, const T* x, int n
 }
 
 template <typename T, typename Grp>
-HSR_HD void ls_eval(const ModelT<T>& m, const WS<T>& w, const Grp& g, int nlimit, int ncon, T alpha, T q1, T q2, T& c,
+HSR_HDC void ls_eval(const ModelT<T>& m, const WS<T>& w, const Grp& g, int nlimit, int ncon, T alpha, T q1, T q2, T& c,
                     T& d1, T& d2) {
   T lc = 0, l1 = 0, l2 = 0;
   for (int i = g.lane; i < nlimit; i += Grp::G) {
@@ -1060,7 +1075,7 @@ HSR_HD void ls_eval(const ModelT<T>& m, const WS<T>& w, const Grp& g, int nlimit
 
 // exact line search along w.search (safeguarded Newton on the 1-D derivative with bracketing)
 template <typename T, typename Grp>
-HSR_HD T linesearch(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, T gtol) {
+HSR_HDC T linesearch(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, T gtol) {
   int nv = m.nv;
   T a1 = 0, a2 = 0;
   for (int i = g.lane; i < nv; i += Grp::G) {
@@ -1118,7 +1133,7 @@ HSR_HD T linesearch(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int 
 
 // Newton solver on the primal convex cost; on exit w.qacc, w.force (and w.tmpv = J^T force) are final.
 template <typename T, typename Grp>
-HSR_HD void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc) {
+HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc) {
   int nv = m.nv;
   if (nefc == 0) {
     for (int i = g.lane; i < nv; i += Grp::G) { w.qacc[i] = w.qacc_smooth[i]; w.tmpv[i] = 0; }
@@ -1218,7 +1233,7 @@ HSR_HD void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit,
 
 // ------------------------------------------------------------------------------------------------ B.8 Euler
 template <typename T>
-HSR_HD void euler_lane0(const ModelT<T>& m, WS<T>& w) {
+HSR_HDC void euler_lane0(const ModelT<T>& m, WS<T>& w) {
   int nv = m.nv;
   T dt = m.timestep;
   // qacc_int = (M + dt*diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
@@ -1261,7 +1276,7 @@ HSR_HD void euler_lane0(const ModelT<T>& m, WS<T>& w) {
 // Algorithmic flop count of one substep: the stage formulas of SURVEY.md §8(d) evaluated with the substep's actual
 // contact / row / iteration / line-search counts (what bench.py's FP32 roofline numerator is made of).
 template <typename T>
-HSR_HD int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls, int npflop) {
+HSR_HDC int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls, int npflop) {
   int nv = m.nv, nb = m.nbody - 1, nfree = m.nblock;
   bool articulated = false;  // any joint other than world-attached slides / free joints => M varies with qpos
   for (int j = 0; j < m.njnt; j++)
@@ -1283,7 +1298,7 @@ HSR_HD int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls,
 
 // mj_forward up to and including the constraint solve (sim.forward(), /root/reference/hsr/env.py:176)
 template <typename T, typename Grp>
-HSR_HD void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+HSR_HDC void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   HSR_PHASE_START(w, g);
   if (g.lane == 0) kinematics_lane0(m, w);
   g.sync();
@@ -1368,7 +1383,7 @@ HSR_HD size_t debug_size(const ModelT<T>& m) {
          (size_t)m.nefc_max * (m.nv + 3) + (size_t)m.nq + m.nv;
 }
 template <typename T>
-HSR_HD void debug_dump(const ModelT<T>& m, const WS<T>& w, double* o) {
+HSR_HDC void debug_dump(const ModelT<T>& m, const WS<T>& w, double* o) {
   size_t k = 0;
   int nv = m.nv;
   o[k++] = w.wi[WI_NCON]; o[k++] = w.wi[WI_NEFC]; o[k++] = w.wi[WI_NLIMIT]; o[k++] = w.wi[WI_ITER];
@@ -1421,7 +1436,7 @@ HSR_HD float uniform32(uint32_t x, float lo, float hi) {
 // mj_resetData + HSREnv.reset_model (/root/reference/hsr/mujoco_env.py:83-85, hsr/env.py:158-177) for one env.
 // Philox4x32-10, key = (seed_lo, global env id), counter = (episode, draw block, seed_hi, 0).  lane 0 only.
 template <typename T>
-HSR_HD void reset_lane0(const ModelT<T>& m, const EnvCfg<T>& cfg, WS<T>& w, uint64_t seed, uint32_t env_id,
+HSR_HDC void reset_lane0(const ModelT<T>& m, const EnvCfg<T>& cfg, WS<T>& w, uint64_t seed, uint32_t env_id,
                         uint32_t episode) {
   for (int i = 0; i < m.nq; i++) w.qpos[i] = m.qpos0[i];
   for (int i = 0; i < m.nv; i++) { w.qvel[i] = 0; w.warm[i] = 0; }

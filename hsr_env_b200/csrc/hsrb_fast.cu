@@ -1,4 +1,5 @@
 // Fast-path action kernel instantiations (hsrb_fast.cuh): 8 lanes per environment, NV = 8 (one block) and 2 (none).
+#define HSR_COMPACT 1
 #include "hsrb_fast.cuh"
 
 template <int NV>
