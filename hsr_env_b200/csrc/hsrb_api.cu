@@ -16,10 +16,10 @@
 #include <string>
 
 #include "../../include/hsrb.h"
-#include "hsrb_fast.cuh"
+#include "hsrb_push.cuh"
 
-cudaError_t hsrb_fast_prepare(int nv, size_t smem, int threads, int* bps);
-cudaError_t hsrb_fast_launch(int nv, const KArgs& a, const FastInfo& f, int grid, int threads, size_t smem, cudaStream_t s);
+cudaError_t hsrb_push_prepare(int G, int nv, size_t smem, int threads, int* bps);
+cudaError_t hsrb_push_launch(int G, int nv, const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s);
 
 namespace {
 
@@ -62,12 +62,14 @@ struct hsrb {
   int* d_taken = nullptr;
   cudaStream_t host_stream = nullptr;
   long long launches = 0;
-  // fast path (hsrb_fast.cuh)
-  FastInfo fast;
+  // fast path (hsrb_push.cuh): sliding base + at most one free box
+  PushInfo fast;
+  PushTables fast_tab;
+  unsigned char* d_fast_tab = nullptr;
   bool fast_ok = false;
   int path = 0;             // 0 auto, 1 general kernel, 2 fast kernel
   bool fast_configured = false;
-  int fast_threads = 0, fast_grid = 0, fast_bps = 0;
+  int fast_lanes = 8, fast_threads = 0, fast_grid = 0, fast_bps = 0;
   unsigned fast_ws = 0;
   char fast_why[128] = "";
 };
@@ -122,81 +124,26 @@ int configure(hsrb* h) {
   return 0;
 }
 
-// Is the model in the family the register-resident kernel handles?  One world-attached body carrying exactly two
-// slide joints (constant orientation), optionally one world-attached free box whose frame is its principal-axis
-// frame, actuators only on the slides.  Fills FastInfo from the host copy of the model.
-bool fill_fast_info(hsrb* h) {
-  const ModelT<float>& m = h->hm.m;
-  FastInfo& f = h->fast;
-  memset(&f, 0, sizeof(f));
-  auto no = [&](const char* why) { snprintf(h->fast_why, sizeof(h->fast_why), "%s", why); return false; };
-  if (m.nbody != 2 && m.nbody != 3) return no("needs 1 robot body and at most 1 block");
-  if (m.body_parent[1] != 0 || m.body_jntnum[1] != 2) return no("robot body must carry exactly two joints");
-  for (int j = 0; j < 2; j++)
-    if (m.jnt_type[j] != JNT_SLIDE || m.jnt_dofadr[j] != j || m.jnt_qposadr[j] != j) return no("robot joints must be slides");
-  f.robot_body = 1; f.block_body = -1; f.nv = 2;
-  if (m.nbody == 3) {
-    int j = m.body_jntadr[2];
-    if (m.body_parent[2] != 0 || m.body_jntnum[2] != 1 || m.jnt_type[j] != JNT_FREE) return no("second body must be a free body");
-    if (m.jnt_qposadr[j] != 2 || m.jnt_dofadr[j] != 2) return no("unexpected dof layout");
-    if (m.body_ipos[6] != 0 || m.body_ipos[7] != 0 || m.body_ipos[8] != 0) return no("block frame must sit at its CoM");
-    if (m.body_inertia[15] != 0 || m.body_inertia[16] != 0 || m.body_inertia[17] != 0) return no("block frame must be principal");
-    f.block_body = 2; f.nv = 8;
-  }
-  if (m.nv != f.nv || m.nu > 2) return no("unexpected nv / nu");
-  // world-frame slide axes: R(body_quat) * jnt_axis
-  float R[9];
-  quat2mat(m.body_quat + 4, R);
-  for (int j = 0; j < 2; j++) {
-    V3<float> ax = mulv(R, ld3(m.jnt_axis + 3 * j));
-    f.axis[j][0] = ax.x; f.axis[j][1] = ax.y; f.axis[j][2] = ax.z;
-  }
-  float dot01 = f.axis[0][0] * f.axis[1][0] + f.axis[0][1] * f.axis[1][1] + f.axis[0][2] * f.axis[1][2];
-  if (fabsf(dot01) > 1e-7f) return no("slide axes must be orthogonal (diagonal mass matrix)");
-  for (int j = 0; j < 2; j++) {
-    f.Mdiag[j] = m.body_mass[1];
-    f.damp[j] = m.dof_damping[j];
-    f.gq[j] = m.body_mass[1] * (m.gravity[0] * f.axis[j][0] + m.gravity[1] * f.axis[j][1] + m.gravity[2] * f.axis[j][2]);
-    f.q0[j] = m.qpos0[j];
-    f.limited[j] = m.jnt_limited[j];
-    f.range[j][0] = m.jnt_range[2 * j]; f.range[j][1] = m.jnt_range[2 * j + 1];
-    for (int k = 0; k < 2; k++) f.lsolref[j][k] = m.jnt_solref[2 * j + k];
-    for (int k = 0; k < 5; k++) f.lsolimp[j][k] = m.jnt_solimp[5 * j + k];
-    f.linvw[j] = m.dof_invweight0[j];
-  }
-  if (f.nv == 8) {
-    for (int k = 0; k < 3; k++) { f.Mdiag[2 + k] = m.body_mass[2]; f.Mdiag[5 + k] = m.body_inertia[12 + k]; }
-    for (int k = 0; k < 6; k++) f.damp[2 + k] = m.dof_damping[2 + k];
-  }
-  f.act_n = m.nu;
-  for (int k = 0; k < m.nu; k++) {
-    if (m.act_dof[k] > 1) return no("actuators must drive the slides");
-    f.act_dof[k] = m.act_dof[k]; f.act_q[k] = m.act_qposadr[k];
-    f.kp[k] = m.act_kp[k]; f.gear[k] = m.act_gear[k];
-    f.cr_lo[k] = m.act_ctrlrange[2 * k]; f.cr_hi[k] = m.act_ctrlrange[2 * k + 1];
-    f.fr_lo[k] = m.act_forcerange[2 * k]; f.fr_hi[k] = m.act_forcerange[2 * k + 1];
-    f.ctrllimited[k] = m.act_ctrllimited[k]; f.forcelimited[k] = m.act_forcelimited[k];
-  }
-  for (int k = 0; k < 3; k++) f.gravity[k] = m.gravity[k];
-  // every contact must involve at most {world, robot, block}: true by construction (nbody <= 3)
-  h->fast_why[0] = 0;
-  return true;
-}
-
 int configure_fast(hsrb* h) {
   if (h->fast_configured) return 0;
   ModelT<float> mm = h->dm;
-  h->fast_ws = (unsigned)ws_carve_fast(mm, nullptr, nullptr);
-  // warps per block so that all environments are resident in one wave when they fit: n / (4 envs/warp) / SMs
-  int warps_needed = (h->n + 3) / 4;
+  h->fast_ws = (unsigned)push::carve(mm, nullptr, nullptr);
+  // lanes per environment: the caller's choice (hsrb_config) when it is one this kernel has, else 8
+  const int G = (h->lanes_req == 8 || h->lanes_req == 16 || h->lanes_req == 32) ? h->lanes_req : 8;
+  h->fast_lanes = G;
+  const int epw = 32 / G;
+  // warps per block so that all environments are resident in one wave when they fit: n / (envs per warp) / SMs
+  int warps_needed = (h->n + epw - 1) / epw;
   int wpb = (warps_needed + h->num_sm - 1) / h->num_sm;
   if (wpb < 1) wpb = 1;
   if (wpb > 8) wpb = 8;
+  // shared memory: at most 227 KB per block
+  while (wpb > 1 && (size_t)h->fast_ws * (wpb * epw) > 227 * 1024) wpb--;
   h->fast_threads = 32 * wpb;
-  size_t smem = (size_t)h->fast_ws * (h->fast_threads / 8);
-  CU(hsrb_fast_prepare(h->fast.nv, smem, h->fast_threads, &h->fast_bps));
+  size_t smem = (size_t)h->fast_ws * (h->fast_threads / G);
+  CU(hsrb_push_prepare(G, h->fast.nv, smem, h->fast_threads, &h->fast_bps));
   if (h->fast_bps < 1) return fail(-3, "fast kernel does not fit on an SM (%zu bytes of shared memory)", smem);
-  int epb = h->fast_threads / 8;
+  int epb = h->fast_threads / G;
   int need = (h->n + epb - 1) / epb;
   int cap = h->fast_bps * h->num_sm;
   h->fast_grid = need < cap ? need : cap;
@@ -217,9 +164,9 @@ int run(hsrb* h, KArgs& a, void* stream) {
     int rc = configure_fast(h);
     if (rc) return rc;
     a.ws_bytes = h->fast_ws;
-    a.m.ncon_max = HSRB_FAST_MAXCON; a.m.nefc_max = 2 + 6 * HSRB_FAST_MAXCON;
-    size_t smem = (size_t)h->fast_ws * (h->fast_threads / 8);
-    CU(hsrb_fast_launch(h->fast.nv, a, h->fast, h->fast_grid, h->fast_threads, smem, (cudaStream_t)stream));
+    a.m.ncon_max = PUSH_MAXCON; a.m.nefc_max = 2 + PUSH_ROWS;
+    size_t smem = (size_t)h->fast_ws * (h->fast_threads / h->fast_lanes);
+    CU(hsrb_push_launch(h->fast_lanes, h->fast.nv, a, h->fast, h->fast_grid, h->fast_threads, smem, (cudaStream_t)stream));
     h->launches++;
     return 0;
   }
@@ -308,7 +255,13 @@ int hsrb_create(const void* model_blob, size_t bytes, int n_envs, int device, ui
     CUH(cudaMemcpy(h->d_state, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice));
   }
 #undef CUH
-  h->fast_ok = fill_fast_info(h);
+  h->fast_ok = push_fill_info(h->hm.m, h->fast, h->fast_tab, h->fast_why, sizeof(h->fast_why));
+  if (h->fast_ok) {
+    cudaError_t e2 = cudaMalloc(&h->d_fast_tab, h->fast_tab.bytes());
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(h->d_fast_tab, h->fast_tab.tab.data(), h->fast_tab.bytes(), cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) { int rc_ = fail(-2, "fast-path tables: %s", cudaGetErrorString(e2)); hsrb_destroy(h); return rc_; }
+    h->fast_tab.point(h->fast, h->d_fast_tab);
+  }
   *out = h;
   return 0;
 }
@@ -324,7 +277,7 @@ int hsrb_set_path(hsrb_t* h, int path) {
 int hsrb_destroy(hsrb_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_episode); cudaFree(h->d_stats);
+  cudaFree(h->d_fast_tab); cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_episode); cudaFree(h->d_stats);
   cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_taken);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   delete h;
@@ -349,6 +302,7 @@ int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max) {
   if (ncon_max > 0) h->dm.ncon_max = h->hm.m.ncon_max = ncon_max;
   if (nefc_max > 0) h->dm.nefc_max = h->hm.m.nefc_max = nefc_max;
   h->configured = false;
+  h->fast_configured = false;
   CU(cudaSetDevice(h->device));
   return configure(h);
 }
@@ -491,7 +445,7 @@ int hsrb_launch_info(hsrb_t* h, int* out4) {  // out4: 6 ints
   if (h->fast_ok && h->path != 1) {
     rc = configure_fast(h);
     if (rc) return rc;
-    out4[0] = 8; out4[1] = (int)h->fast_ws; out4[2] = h->fast_bps * (h->fast_threads / 8); out4[3] = h->fast_grid;
+    out4[0] = h->fast_lanes; out4[1] = (int)h->fast_ws; out4[2] = h->fast_bps * (h->fast_threads / h->fast_lanes); out4[3] = h->fast_grid;
     out4[4] = 2; out4[5] = h->fast_threads;
     return 0;
   }

@@ -13,6 +13,13 @@
 
 using namespace hsr;
 
+// dynamic shared memory of the block (the SIMT emulator of tests/simt_emu substitutes a host buffer)
+#if defined(HSRB_SIMT_EMU)
+#define HSRB_DYN_SMEM(name) unsigned char* name = emu::dyn_smem
+#else
+#define HSRB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 enum { ST_SUBSTEPS = 0, ST_ITERS, ST_NARROW, ST_LSEVAL, ST_CONTACTS, ST_ROWS, ST_LAUNCHES, ST_BAD, ST_FLOPS, ST_PHASE0, ST_COUNT = ST_PHASE0 + PH_COUNT };
 
 struct KArgs {
@@ -52,7 +59,7 @@ __device__ __forceinline__ void store_state(const KArgs& a, WS<float>& w, const 
 // The action kernel.  blockDim.x = 32 (one warp), 32/G environments per block, grid-stride over environments.
 template <int G>
 __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ KArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  HSRB_DYN_SMEM(smem);
   DevGrp<G> g;
   const int gpb = 32 / G;
   const int gi = threadIdx.x / G;

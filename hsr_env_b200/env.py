@@ -112,7 +112,7 @@ class BatchedHSREnv:
                                          ctypes.byref(self._h)))
         if lanes_per_env:
             _lib.check(self._lib.hsrb_config(self._h, int(lanes_per_env), 0, 0))
-        # "auto": register-resident fast kernel for the sliding-base + <=1 block family, else the general kernel
+        # "auto": fast kernel (hsrb_push.cuh) for the sliding-base + <=1 block family, else the general kernel
         self.kernel_path = _lib.check(self._lib.hsrb_set_path(self._h, {"auto": 0, "general": 1, "fast": 2}[kernel]))
         m = self.model
         self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody

@@ -34,7 +34,7 @@ int hsrb_dims(hsrb_t* h, int* nq, int* nv, int* nu, int* nbody, int* nblock);
  * /root/reference/hsr/models/world.xml:44). */
 int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max);
 
-/* Kernel selection: 0 = auto (the register-resident fast kernel when the model is a sliding base with at most
+/* Kernel selection: 0 = auto (the fast kernel (hsrb_push.cuh) when the model is a sliding base with at most
  * one free box - the README block-push family - else the general kernel), 1 = general kernel, 2 = fast kernel
  * (error if the model is outside that family).  Returns the path that will run (1 or 2). */
 int hsrb_set_path(hsrb_t* h, int path);
