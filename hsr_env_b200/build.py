@@ -27,14 +27,16 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, phase_clocks: bool = False) -> Path:
-    """phase_clocks=True builds the instrumented variant libhsrb_prof.so (-DHSRB_PHASE_CLOCKS)."""
+def build(force: bool = False, verbose: bool = False, phase_clocks: bool = False, defines=(), tag: str = "") -> Path:
+    """phase_clocks=True builds the instrumented variant libhsrb_prof.so (-DHSRB_PHASE_CLOCKS); ``defines`` + ``tag``
+    build an experiment variant libhsrb_<tag>.so with extra -D flags (selected at run time with HSRB_LIB)."""
     hdrs = [CSRC / h for h in HEADERS]
     objs = []
     jobs = []
-    tag = ".prof" if phase_clocks else ""
-    flags = FLAGS + (["-DHSRB_PHASE_CLOCKS"] if phase_clocks else [])
-    lib = CSRC / "libhsrb_prof.so" if phase_clocks else LIB
+    name = tag
+    tag = ".prof" if phase_clocks else (f".{tag}" if tag else "")
+    flags = FLAGS + (["-DHSRB_PHASE_CLOCKS"] if phase_clocks else []) + [f"-D{d}" for d in defines]
+    lib = CSRC / "libhsrb_prof.so" if phase_clocks else (CSRC / f"libhsrb_{name}.so" if name else LIB)
     for tu in TUS:
         src = CSRC / tu
         obj = CSRC / (src.stem + tag + ".o")
@@ -63,4 +65,8 @@ def build(force: bool = False, verbose: bool = False, phase_clocks: bool = False
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_clocks="--prof" in sys.argv))
+    defs = [a.split("=", 1)[1] if a.startswith("--define=") else None for a in sys.argv]
+    defs = [d for d in defs if d]
+    tags = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_clocks="--prof" in sys.argv, defines=defs,
+                tag=tags[0] if tags else ""))

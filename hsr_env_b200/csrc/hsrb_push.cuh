@@ -21,6 +21,11 @@
 #include "hsrb_kernels.cuh"
 
 #define PUSH_MAXCON 8
+// PUSH_PHASE_LOCK: block-wide barriers between the phases of a substep, so that every warp of the SM runs the same
+// code region at the same time (instruction-cache locality) at the price of waiting for the slowest warp per phase
+#ifndef PUSH_PHASE_LOCK
+#define PUSH_PHASE_LOCK 0
+#endif
 #define PUSH_ROWS (6 * PUSH_MAXCON)   // fixed stride of 6 rows per contact; rows >= condim are zero rows
 
 // Model constants of this kernel family, filled on the host (push_fill_info) and passed by value as a kernel
@@ -242,75 +247,86 @@ template <int G>
 __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInfo& fi, push::Ws& s, WS<float>& w,
                                            const DevGrp<G>& g) {
   int ncon = 0, nrow = 0, narrow = 0, npflop = 0;
-  for (int base = 0; base < m.npair; base += G) {
-    const int k = base + g.lane;
-    bool hit = false;
-    if (k < m.npair) {
-      const int a = m.pair_geom1[k], b = m.pair_geom2[k];
-      const V3<float> dp = cvt<float>(ld3(s.gpos + 3 * b) - ld3(s.gpos + 3 * a));
-      if (m.geom_type[a] == GEOM_PLANE) {
-        const double* Ma = fi.gmatw + 9 * a;  // planes are static: world orientation is a table entry
-        hit = dot(dp, mk<float>((float)Ma[2], (float)Ma[5], (float)Ma[8])) <= m.geom_rbound[b];
-      } else {
-        const float rr = m.geom_rbound[a] + m.geom_rbound[b];
-        hit = dot(dp, dp) <= rr * rr;
-        const float* ha = s.gaabb + 3 * a; const float* hb = s.gaabb + 3 * b;
-        hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
-      }
-    }
-    unsigned bits = g.ballot(hit);
-    while (bits) {
-      const int l = __ffs((int)bits) - 1;
-      bits &= bits - 1;
-      const int pk = base + l;
-      const int func = m.pair_func[pk];
-      narrow++;
-      npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
-      if (func == NP_PLANE_BOX) {
-        // mjc_PlaneBox: one corner per lane; the first four penetrating corners (corner order) become contacts
-        const int ga = m.pair_geom1[pk], gb = m.pair_geom2[pk];
-        const double* Ma = fi.gmatw + 9 * ga;
-        const V3<GT> n = mk<GT>(Ma[2], Ma[5], Ma[8]);
-        const V3<GT> pb = ld3(s.gpos + 3 * gb);
-        const GT dist0 = dot(pb - ld3(s.gpos + 3 * ga), n);
-        const int i = g.lane;
-        const float* sz = m.geom_size + 3 * gb;
-        const V3<GT> c = mk<GT>((i & 1) ? (GT)sz[0] : -(GT)sz[0], (i & 2) ? (GT)sz[1] : -(GT)sz[1], (i & 4) ? (GT)sz[2] : -(GT)sz[2]);
-        // geom orientation in the world: table entry (static / robot geoms) or xmat(block) * geom_mat, applied to the
-        // corner as matrix-vector products
-        V3<GT> vec = mulv(fi.gmatw + 9 * gb, c);
-        if (fi.gmove[gb] == 2) vec = mulv(s.xmat + 9 * m.geom_body[gb], vec);
-        const GT ld = dot(n, vec);
-        const bool pen = i < 8 && !(dist0 + ld > 0 || ld > 0);
-        const unsigned pm = g.ballot(pen);
-        const int rank = __popc(pm & ((1u << i) - 1u));
-        int nh = __popc(pm);
-        if (nh > 4) nh = 4;
-        const int room = m.ncon_max - ncon;
-        if (pen && rank < nh && rank < room) {
-          const int slot = ncon + rank;
-          const GT dist = dist0 + ld;
-          s.con_pair[slot] = pk; s.con_dist[slot] = (float)dist;
-          st3c(s.con_pos + 3 * slot, pb + vec - n * (dist * GT(0.5)));
-          make_frame(n, s.con_frame + 9 * slot);
-        }
-        if (nh > room) { nh = room; if (g.lane == 0) s.wi[WI_FLAGS] |= FLAG_CON_OVERFLOW; }
-        ncon += nh;
-      } else {
-        Geom<float> A, B;
-        load_geom(m, w, m.pair_geom1[pk], A);
-        load_geom(m, w, m.pair_geom2[pk], B);
-        if (func == NP_PLANE_CONVEX) {
-          const V3<GT> n = mcol(A.mat, 2);
-          const V3<GT> p = support_d(B, -n, g);
-          const GT dist = dot(p - A.pos, n);
-          if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * GT(0.5)), n);
-        } else if (func == NP_BOX_BOX) {
-          box_box(m, w, g, ncon, nrow, pk, A, B);
+  for (int base = 0; base < m.npair; base += 32) {
+    // cull up to 32 candidate pairs (G per round, one pair per lane) into this environment's job mask
+    unsigned bits = 0;
+    for (int k0 = 0; k0 < 32 && base + k0 < m.npair; k0 += G) {
+      const int k = base + k0 + g.lane;
+      bool hit = false;
+      if (k < m.npair) {
+        const int a = m.pair_geom1[k], b = m.pair_geom2[k];
+        const V3<float> dp = cvt<float>(ld3(s.gpos + 3 * b) - ld3(s.gpos + 3 * a));
+        if (m.geom_type[a] == GEOM_PLANE) {
+          const double* Ma = fi.gmatw + 9 * a;  // planes are static: world orientation is a table entry
+          hit = dot(dp, mk<float>((float)Ma[2], (float)Ma[5], (float)Ma[8])) <= m.geom_rbound[b];
         } else {
-          GT depth; V3<GT> dir, pos;
-          if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
-            add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
+          const float rr = m.geom_rbound[a] + m.geom_rbound[b];
+          hit = dot(dp, dp) <= rr * rr;
+          const float* ha = s.gaabb + 3 * a; const float* hb = s.gaabb + 3 * b;
+          hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
+        }
+      }
+      bits |= g.ballot(hit) << k0;
+    }
+#if PUSH_PHASE_LOCK
+    __syncthreads();
+#endif
+    // narrowphase jobs in pair order; the environments of a warp take their k-th job in the same round, so that
+    // groups running the same routine (plane-box, portal refinement) execute it converged instead of one after the other
+    while (__any_sync(0xffffffffu, bits != 0)) {
+      if (bits) {
+        const int l = __ffs((int)bits) - 1;
+        bits &= bits - 1;
+        const int pk = base + l;
+        const int func = m.pair_func[pk];
+        narrow++;
+        npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
+        if (func == NP_PLANE_BOX) {
+          // mjc_PlaneBox: one corner per lane; the first four penetrating corners (corner order) become contacts
+          const int ga = m.pair_geom1[pk], gb = m.pair_geom2[pk];
+          const double* Ma = fi.gmatw + 9 * ga;
+          const V3<GT> n = mk<GT>(Ma[2], Ma[5], Ma[8]);
+          const V3<GT> pb = ld3(s.gpos + 3 * gb);
+          const GT dist0 = dot(pb - ld3(s.gpos + 3 * ga), n);
+          const int i = g.lane;
+          const float* sz = m.geom_size + 3 * gb;
+          const V3<GT> c = mk<GT>((i & 1) ? (GT)sz[0] : -(GT)sz[0], (i & 2) ? (GT)sz[1] : -(GT)sz[1], (i & 4) ? (GT)sz[2] : -(GT)sz[2]);
+          // geom orientation in the world: table entry (static / robot geoms) or xmat(block) * geom_mat, applied to the
+          // corner as matrix-vector products
+          V3<GT> vec = mulv(fi.gmatw + 9 * gb, c);
+          if (fi.gmove[gb] == 2) vec = mulv(s.xmat + 9 * m.geom_body[gb], vec);
+          const GT ld = dot(n, vec);
+          const bool pen = i < 8 && !(dist0 + ld > 0 || ld > 0);
+          const unsigned pm = g.ballot(pen);
+          const int rank = __popc(pm & ((1u << i) - 1u));
+          int nh = __popc(pm);
+          if (nh > 4) nh = 4;
+          const int room = m.ncon_max - ncon;
+          if (pen && rank < nh && rank < room) {
+            const int slot = ncon + rank;
+            const GT dist = dist0 + ld;
+            s.con_pair[slot] = pk; s.con_dist[slot] = (float)dist;
+            st3c(s.con_pos + 3 * slot, pb + vec - n * (dist * GT(0.5)));
+            make_frame(n, s.con_frame + 9 * slot);
+          }
+          if (nh > room) { nh = room; if (g.lane == 0) s.wi[WI_FLAGS] |= FLAG_CON_OVERFLOW; }
+          ncon += nh;
+        } else {
+          Geom<float> A, B;
+          load_geom(m, w, m.pair_geom1[pk], A);
+          load_geom(m, w, m.pair_geom2[pk], B);
+          if (func == NP_PLANE_CONVEX) {
+            const V3<GT> n = mcol(A.mat, 2);
+            const V3<GT> p = support_d(B, -n, g);
+            const GT dist = dot(p - A.pos, n);
+            if (dist <= 0) add_contact(m, w, g, ncon, nrow, pk, dist, p - n * (dist * GT(0.5)), n);
+          } else if (func == NP_BOX_BOX) {
+            box_box(m, w, g, ncon, nrow, pk, A, B);
+          } else {
+            GT depth; V3<GT> dir, pos;
+            if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+              add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
+          }
         }
       }
     }
@@ -341,7 +357,15 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
   const float scale = 1.0f / (m.meaninertia * (float)(NV > 1 ? NV : 1));
   const int epb = blockDim.x / G;
 
-  for (int env = blockIdx.x * epb + gi; env < a.n; env += gridDim.x * epb) {
+  // Control flow is uniform across the warp: every group runs the same number of environment rounds and substeps,
+  // and the data-dependent loops (narrowphase jobs, Newton iterations) are voted on by the whole warp, so that the
+  // groups of a warp execute each phase together instead of drifting apart and being issued one after the other.
+  // A group without an environment (tail of the batch) or whose environment has finished its action keeps computing
+  // on a copy; its results were written when it finished and nothing is stored afterwards.
+  constexpr unsigned FULL = 0xffffffffu;
+  for (int env0 = blockIdx.x * epb; env0 < a.n; env0 += gridDim.x * epb) {
+    const bool valid = env0 + gi < a.n;
+    const int env = valid ? env0 + gi : a.n - 1;
     // ------------------------------------------------------------------ state -> registers (replicated)
     float qpos[9], qvel[8], warm[8], ctrl[2], mocap[3];
 #pragma unroll
@@ -370,10 +394,29 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
     }
     int n_iter = 0, n_ls = 0, sumcon = 0, sumefc = 0, kflop = 0, flags = 0;
     bool success = false;
+    bool finished = !valid || a.nsub <= 0;   // results written (or nothing to write)
     int taken = 0;
     g.sync();
+    if (valid && a.nsub <= 0) {
+      // no substeps requested: the observation is the current state
+      float* st = a.state + (size_t)env * a.S;
+      const int nobs = nq + NV;
+      for (int i = g.lane; i < nobs; i += G) if (a.obs) a.obs[(size_t)env * nobs + i] = st[i];
+      if (g.lane == 0) {
+        if (a.reward) a.reward[env] = 0.f;
+        if (a.done) a.done[env] = 0;
+        if (a.success) a.success[env] = 0;
+        if (a.taken) a.taken[env] = 0;
+        if (a.bad) a.bad[env] = 0;
+      }
+    }
 
     for (int sb_ = 0; sb_ < a.nsub; sb_++) {
+#if PUSH_PHASE_LOCK
+      if (__syncthreads_and(finished)) break;
+#else
+      if (__all_sync(FULL, finished)) break;
+#endif
       HSR_PHASE_START(s, g);
       // ---------------------------------------------------------------- poses (B.1), geometry in double
       GT xb[3] = {0, 0, 0}, Rb[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -438,7 +481,11 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
       }
       // ---------------------------------------------------------------- collision (B.3)
       int ncon = push_collision<G>(m, fi, s, w, g);
+#if PUSH_PHASE_LOCK
+      __syncthreads();
+#else
       g.sync();
+#endif
       if (ncon > PUSH_MAXCON) ncon = PUSH_MAXCON;
       flags |= s.wi[WI_FLAGS];
       HSR_PHASE(s, g, PH_COLLIDE);
@@ -638,7 +685,9 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
         return gs;
       };
 
-      if (nefc_true == 0) {
+      bool solving = nefc_true != 0;
+      float cost = 0.f;
+      if (!solving) {
 #pragma unroll
         for (int i = 0; i < NV; i++) x[i] = as[i];
       } else {
@@ -659,9 +708,16 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
           rows_jar(x);
           g.sync();
         }
-        float cost = g.sum(cone(true)) + gauss_of(x) + limit_cost(x);
+        cost = g.sum(cone(true)) + gauss_of(x) + limit_cost(x);
         g.sync();
-        while (true) {
+      }
+      // Newton iterations: the loop is voted on by the whole warp so that its groups stay in step
+      while (__any_sync(FULL, solving)) {
+        if (solving) {
+          bool stop = false;
+          float srch[8], sn = 0.f, dec = 0.f, alpha = 0.f, gtol = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; i++) srch[i] = 0.f;
           // ---- gradient component of this lane's dof: M x - qfrc_smooth - J^T f
           float myx = 0.f, myqs = 0.f, myM = 0.f;
 #pragma unroll
@@ -685,16 +741,8 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
 #pragma unroll
           for (int o = 1; o < 8; o <<= 1) gn += __shfl_xor_sync(g.mask, gn, o);
           gn = sqrtf(gn);
-          if (it > 0 && scale * gn < m.tolerance) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf, i, G);
-            break;
-          }
-          if (it >= m.iterations) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf, i, G);
-            break;
-          }
+          if ((it > 0 && scale * gn < m.tolerance) || it >= m.iterations) stop = true;
+          if (!stop) {
           // ---- W rows (rows across lanes): zone 1 -> D J, zone 2 -> cone Hessian block times the contact's rows
           if (zone == 2) {
             float* hc = s.Hc + 36 * g.lane;
@@ -804,10 +852,8 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
             if (li == k) sv = xk;
             acc -= Lc[k] * xk;                                  // meaningful for li < k
           }
-          float srch[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) srch[i] = (i < NV) ? __shfl_sync(g.mask, sv, i, G) : 0.f;
-          float sn = 0.f, dec = 0.f;
           {
             float dd = (li < NV) ? -grad * sv : 0.f;
 #pragma unroll
@@ -817,11 +863,9 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < NV; i++) sn += srch[i] * srch[i];
           sn = sqrtf(sn);
-          if (sn < 1e-15f) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf, i, G);
-            break;
-          }
+          if (sn < 1e-15f) stop = true;
+          }  // !stop: search direction
+          if (!stop) {
           // ---- jv = J search (rows across lanes)
           for (int r = g.lane; r < nr; r += G) {
             const push::F8 j = push::ld8(s.J + 8 * r);
@@ -831,7 +875,7 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
             s.jv[r] = accv;
           }
           g.sync();
-          const float gtol = m.tolerance * m.ls_tolerance * sn / scale;
+          gtol = m.tolerance * m.ls_tolerance * sn / scale;
           // ---- exact line search: root of the 1-D derivative (safeguarded Newton with bracketing)
           float q1 = 0.f, q2 = 0.f;
 #pragma unroll
@@ -889,7 +933,6 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
             d1 = l1 + q1 + 2 * alpha * q2;
             d2 = l2 + 2 * q2;
           };
-          float alpha = 0.f;
           {
             float d1, d2;
             ls_eval(0.f, d1, d2);
@@ -918,11 +961,9 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
               else alpha = lo;
             }
           }
-          if (alpha == 0.f) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf, i, G);
-            break;
-          }
+          if (alpha == 0.f) stop = true;
+          }  // !stop: line search
+          if (!stop) {
 #pragma unroll
           for (int i = 0; i < NV; i++) x[i] += alpha * srch[i];
           for (int r = g.lane; r < nr; r += G) s.jar[r] += alpha * s.jv[r];
@@ -943,12 +984,21 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
               const float jr = lim_sg[j] * x[j] - lim_aref[j];
               if (jr < 0 && li == j) qf2 += lim_sg[j] * (-lim_D[j] * jr);
             }
+            qf = qf2;
+            stop = true;
+          }
+          }  // !stop: update
+          if (stop) {
+            // qfrc_constraint of the final point, replicated for the integrator
 #pragma unroll
-            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf2, i, G);
-            break;
+            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf, i, G);
+            solving = false;
           }
         }
       }
+#if PUSH_PHASE_LOCK
+      __syncthreads();
+#endif
       HSR_PHASE(s, g, PH_SOLVE);
       n_iter += it; n_ls += ls_used;
       kflop += algorithmic_flops(m, ncon, nefc_true, it, ls_used, s.wi[WI_NPFLOP]);
@@ -981,42 +1031,44 @@ __global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ 
         }
         quatnormalize(qpos + 5);
       }
-      taken++;
       g.sync();
       HSR_PHASE(s, g, PH_EULER);
-      if (reached) { success = true; break; }
-    }
-
-    // ------------------------------------------------------------------ results: HBM once per action
-    {
-      float* st = a.state + (size_t)env * a.S;
-      const int nobs = nq + NV;
-      for (int i = g.lane; i < nq + 2 * NV; i += G) {
-        float v = 0.f;
+      if (!finished) {
+        taken++;
+        if (reached) success = true;
+        if (reached || sb_ == a.nsub - 1) {
+          // ---------------------------------------------------------------- results: HBM once per action
+          finished = true;
+          float* st = a.state + (size_t)env * a.S;
+          const int nobs = nq + NV;
+          for (int i = g.lane; i < nq + 2 * NV; i += G) {
+            float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < (HASB ? 9 : 2); k++) if (i == k) v = qpos[k];
+            for (int k = 0; k < (HASB ? 9 : 2); k++) if (i == k) v = qpos[k];
 #pragma unroll
-        for (int k = 0; k < NV; k++) { if (i == nq + k) v = qvel[k]; if (i == nq + NV + k) v = warm[k]; }
-        st[i] = v;
-        if (a.obs && i < nobs) a.obs[(size_t)env * nobs + i] = v;
-      }
-      if (g.lane == 0) {
-        if (a.reward) a.reward[env] = success ? 1.0f : 0.0f;
-        if (a.done) a.done[env] = success ? 1 : 0;
-        if (a.success) a.success[env] = success ? 1 : 0;
-        if (a.taken) a.taken[env] = taken;
-        if (a.bad) a.bad[env] = (unsigned char)flags;
-        atomicAdd(a.stats + ST_SUBSTEPS, (unsigned long long)taken);
-        atomicAdd(a.stats + ST_ITERS, (unsigned long long)n_iter);
-        atomicAdd(a.stats + ST_NARROW, (unsigned long long)s.wi[WI_NARROW]);
-        atomicAdd(a.stats + ST_LSEVAL, (unsigned long long)n_ls);
-        atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)sumcon);
-        atomicAdd(a.stats + ST_ROWS, (unsigned long long)sumefc);
-        atomicAdd(a.stats + ST_FLOPS, (unsigned long long)kflop);
-        if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
+            for (int k = 0; k < NV; k++) { if (i == nq + k) v = qvel[k]; if (i == nq + NV + k) v = warm[k]; }
+            st[i] = v;
+            if (a.obs && i < nobs) a.obs[(size_t)env * nobs + i] = v;
+          }
+          if (g.lane == 0) {
+            if (a.reward) a.reward[env] = success ? 1.0f : 0.0f;
+            if (a.done) a.done[env] = success ? 1 : 0;
+            if (a.success) a.success[env] = success ? 1 : 0;
+            if (a.taken) a.taken[env] = taken;
+            if (a.bad) a.bad[env] = (unsigned char)flags;
+            atomicAdd(a.stats + ST_SUBSTEPS, (unsigned long long)taken);
+            atomicAdd(a.stats + ST_ITERS, (unsigned long long)n_iter);
+            atomicAdd(a.stats + ST_NARROW, (unsigned long long)s.wi[WI_NARROW]);
+            atomicAdd(a.stats + ST_LSEVAL, (unsigned long long)n_ls);
+            atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)sumcon);
+            atomicAdd(a.stats + ST_ROWS, (unsigned long long)sumefc);
+            atomicAdd(a.stats + ST_FLOPS, (unsigned long long)kflop);
+            if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
 #ifdef HSRB_PHASE_CLOCKS
-        for (int k = 0; k < PH_COUNT; k++) atomicAdd(a.stats + ST_PHASE0 + k, (unsigned long long)s.wi[WI_PHASE0 + k]);
+            for (int k = 0; k < PH_COUNT; k++) atomicAdd(a.stats + ST_PHASE0 + k, (unsigned long long)s.wi[WI_PHASE0 + k]);
 #endif
+          }
+        }
       }
     }
     g.sync();

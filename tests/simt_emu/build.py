@@ -15,10 +15,13 @@ DEPS = [HERE / "emu_push.cpp", HERE / "simt_emu.h", ROOT / "hsr_env_b200/csrc/hs
 
 
 def build(force=False):
+    import os
+    extra = os.environ.get("EMU_DEFINES", "").split()
+    force = force or bool(extra)
     LIB.parent.mkdir(exist_ok=True)
     if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return LIB
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-D__CUDACC__", "-DHSRB_SIMT_EMU", "-DHSR_COMPACT",
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-D__CUDACC__", "-DHSRB_SIMT_EMU", "-DHSR_COMPACT", *[f"-D{d}" for d in extra],
            "-include", str(HERE / "simt_emu.h"), "-I", str(HERE), "-o", str(LIB), str(HERE / "emu_push.cpp"), "-lpthread"]
     subprocess.check_call(cmd)
     return LIB

@@ -68,6 +68,7 @@ struct Warp {
 struct Block {
   std::vector<std::unique_ptr<Warp>> warps;
   std::unique_ptr<SpinBarrier> all;
+  std::atomic<int> vote{0};
 };
 
 inline thread_local Block* tl_block = nullptr;
@@ -111,8 +112,19 @@ inline unsigned __ballot_sync(unsigned mask, bool p) {
   b.wait();
   return r;
 }
+inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0; }
+inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) == mask; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::tl_warp->bar(mask).wait(); }
 inline void __syncthreads() { emu::tl_block->all->wait(); }
+inline int __syncthreads_and(int p) {
+  emu::Block& b = *emu::tl_block;
+  b.all->wait();
+  if (threadIdx.x == 0) b.vote.store(0);
+  b.all->wait();
+  if (!p) b.vote.fetch_add(1);
+  b.all->wait();
+  return b.vote.load() == 0;
+}
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline long long clock64() { return 0; }
