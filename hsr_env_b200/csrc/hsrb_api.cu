@@ -136,7 +136,8 @@ int configure_fast(hsrb* h) {
   int warps_needed = (h->n + epw - 1) / epw;
   int wpb = (warps_needed + h->num_sm - 1) / h->num_sm;
   if (wpb < 1) wpb = 1;
-  if (wpb > 8) wpb = 8;
+  const int wpb_max = G == 16 ? 14 : 8;   // __launch_bounds__ of the kernel (hsrb_push.cuh)
+  if (wpb > wpb_max) wpb = wpb_max;
   // shared memory: at most 227 KB per block
   while (wpb > 1 && (size_t)h->fast_ws * (wpb * epw) > 227 * 1024) wpb--;
   h->fast_threads = 32 * wpb;

@@ -24,7 +24,7 @@
 // PUSH_PHASE_LOCK: block-wide barriers between the phases of a substep, so that every warp of the SM runs the same
 // code region at the same time (instruction-cache locality) at the price of waiting for the slowest warp per phase
 #ifndef PUSH_PHASE_LOCK
-#define PUSH_PHASE_LOCK 0
+#define PUSH_PHASE_LOCK 1
 #endif
 #define PUSH_ROWS (6 * PUSH_MAXCON)   // fixed stride of 6 rows per contact; rows >= condim are zero rows
 
@@ -337,7 +337,7 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
 
 // ---------------------------------------------------------------------------------------------------- the kernel
 template <int G, int NV>
-__global__ void __launch_bounds__(256) hsrb_push_kernel(const __grid_constant__ KArgs a, const __grid_constant__ PushInfo fi) {
+__global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __grid_constant__ KArgs a, const __grid_constant__ PushInfo fi) {
   HSRB_DYN_SMEM(smem);
   DevGrp<G> g;
   constexpr bool HASB = NV == 8;
