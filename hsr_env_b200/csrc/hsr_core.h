@@ -137,7 +137,13 @@ template <typename T> HSR_HD V3<T> cross(V3<T> a, V3<T> b) {
   return mk<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 template <typename T> HSR_HD T norm(V3<T> a) { return sqrt(dot(a, a)); }
-template <typename T> HSR_HD V3<T> normalized(V3<T> a) { return a * (T(1) / norm(a)); }
+template <typename T> HSR_HD V3<T> normalized(V3<T> a) {
+#if defined(__CUDA_ARCH__)
+  return a * (T)rsqrt(dot(a, a));   // one special-function sequence instead of sqrt + divide (<= 2 ulp of T)
+#else
+  return a * (T(1) / norm(a));
+#endif
+}
 template <typename T> HSR_HD T comp(V3<T> a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 // 3x3 row-major helpers
 template <typename T> HSR_HD V3<T> mcol(const T* R, int k) { return mk<T>(R[k], R[3 + k], R[6 + k]); }
@@ -472,6 +478,7 @@ HSR_HDC void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
 // ------------------------------------------------------------------------------------------------ B.3 collision
 template <typename T> struct Geom {
   int type; const T* size; const T* verts; int nvert; V3<GT> pos; GT mat[9];
+  const T* verts4 = nullptr;  // optional copy of the hull vertices with a stride of 4 (16-byte aligned): 128-bit loads
 };
 
 template <typename T>
@@ -543,8 +550,32 @@ template <typename T> HSR_HD T origin_tri_dist2(V3<T> a, V3<T> b, V3<T> c, V3<T>
 // compare triple products of vectors that shrink with the penetration depth against libccd's DBL_EPSILON-scale
 // thresholds, which fp32 cannot resolve (a 0.1 mm contact came out with a different face normal).  Only the
 // vertex scan of a hull (the bulk of the work) runs in T; its result is an index, i.e. exact.
+#if defined(__CUDACC__)
+// argmax_i <v_i, l> over a hull stored as float4, lanes of the group striding over the vertices, two vertices per
+// iteration; ties go to the lowest index (as the scalar scan below)
+template <typename Grp>
+__device__ __noinline__ int hull_scan4(const float4* __restrict__ v, int n, float lx, float ly, float lz, const Grp& g) {
+  float best = -FLT_MAX;
+  int bi = 0x7fffffff;
+  int i = g.lane;
+  for (; i + Grp::G < n; i += 2 * Grp::G) {
+    const float4 a = v[i], b = v[i + Grp::G];
+    const float va = a.x * lx + a.y * ly + a.z * lz, vb = b.x * lx + b.y * ly + b.z * lz;
+    if (va > best) { best = va; bi = i; }
+    if (vb > best) { best = vb; bi = i + Grp::G; }
+  }
+  if (i < n) {
+    const float4 a = v[i];
+    const float va = a.x * lx + a.y * ly + a.z * lz;
+    if (va > best) { best = va; bi = i; }
+  }
+  g.argmax(best, bi);
+  return bi;
+}
+#endif
+
 template <typename T, typename Grp>
-HSR_HDC V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
+HSR_HD V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
   typedef double W;
   const W* R = ge.mat;
   V3<W> dl = multv(R, d), res;
@@ -555,6 +586,11 @@ HSR_HDC V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
     W n = sqrt(dl.x * dl.x + dl.y * dl.y);
     res = mk<W>(0, 0, dl.z >= 0 ? (W)ge.size[1] : -(W)ge.size[1]);
     if (n > 1e-15) { res.x = dl.x / n * (W)ge.size[0]; res.y = dl.y / n * (W)ge.size[0]; }
+#if defined(__CUDACC__)
+  } else if (ge.verts4) {
+    const int bi = hull_scan4(reinterpret_cast<const float4*>(ge.verts4), ge.nvert, (float)dl.x, (float)dl.y, (float)dl.z, g);
+    res = mk<W>((W)ge.verts4[4 * bi], (W)ge.verts4[4 * bi + 1], (W)ge.verts4[4 * bi + 2]);
+#endif
   } else {
     T lx = (T)dl.x, ly = (T)dl.y, lz = (T)dl.z;
     T best = -FLT_MAX; int bi = 0x7fffffff;
@@ -568,9 +604,9 @@ HSR_HDC V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
   return ge.pos + mulv(R, res);
 }
 
-// support point of the Minkowski difference g1 - g2 along d (one out-of-line copy: it is called from ~6 sites)
+// support point of the Minkowski difference g1 - g2 along d (inlined: the out-of-line part is the hull scan)
 template <typename T, typename Grp>
-HSR_HDC void mpr_support(const Geom<T>& g1, const Geom<T>& g2, V3<double> d, const Grp& g, Sup<double>& s) {
+HSR_HD void mpr_support(const Geom<T>& g1, const Geom<T>& g2, V3<double> d, const Grp& g, Sup<double>& s) {
   s.v1 = support_d(g1, d, g); s.v2 = support_d(g2, -d, g); s.v = s.v1 - s.v2;
 }
 

@@ -52,17 +52,19 @@ struct PushInfo {
   const int* gmove;       // [ngeom] 0 static, 1 rides on the robot, 2 rides on the block
   const double* pairc;    // [npair][8] k, b, diagApprox, solimp d0, dmax, width, mid, power (clamped as MuJoCo does)
   const double* xmat0;    // [nbody][9] compile-time body orientations (world, robot; the block's is overwritten)
+  const float* verts4;    // [nvert][4] hull vertices padded to 16 bytes (128-bit loads in the support scan)
 };
 
 // Host-side table builder (also used by the emulated build).  Layout of `tab` (doubles):
 //   gbase ngeom*3 | gmatw ngeom*9 | pairc npair*8 | xmat0 nbody*9 | ghalf ngeom*3 (floats, padded) | gmove ngeom (ints, padded)
 struct PushTables {
   std::vector<double> tab;
-  size_t off_gbase, off_gmatw, off_pairc, off_xmat0, off_ghalf, off_gmove;
+  size_t off_gbase, off_gmatw, off_pairc, off_xmat0, off_ghalf, off_gmove, off_verts4;
   void point(PushInfo& f, const unsigned char* base) const {
     f.gbase = (const double*)(base + off_gbase); f.gmatw = (const double*)(base + off_gmatw);
     f.pairc = (const double*)(base + off_pairc); f.xmat0 = (const double*)(base + off_xmat0);
     f.ghalf = (const float*)(base + off_ghalf); f.gmove = (const int*)(base + off_gmove);
+    f.verts4 = (const float*)(base + off_verts4);
   }
   size_t bytes() const { return tab.size() * sizeof(double); }
 };
@@ -146,10 +148,16 @@ inline bool push_fill_info(const ModelT<float>& m, PushInfo& f, PushTables& t, c
   t.off_ghalf = sizeof(double) * nd;
   size_t nhalf_d = ((size_t)ng * 3 * sizeof(float) + 7) / 8, nmove_d = ((size_t)ng * sizeof(int) + 7) / 8;
   t.off_gmove = t.off_ghalf + 8 * nhalf_d;
-  t.tab.assign(nd + nhalf_d + nmove_d, 0.0);
+  t.off_verts4 = t.off_gmove + 8 * nmove_d;
+  t.off_verts4 += (16 - t.off_verts4 % 16) % 16;
+  const size_t nv4_d = ((size_t)m.nvert * 4 * sizeof(float) + 7) / 8 + 2;
+  t.tab.assign(t.off_verts4 / 8 + nv4_d, 0.0);
   double* gbase = t.tab.data(); double* gmatw = gbase + ng * 3; double* pairc = gmatw + ng * 9; double* xmat0 = pairc + np * 8;
   float* ghalf = (float*)((unsigned char*)t.tab.data() + t.off_ghalf);
   int* gmove = (int*)((unsigned char*)t.tab.data() + t.off_gmove);
+  float* verts4 = (float*)((unsigned char*)t.tab.data() + t.off_verts4);
+  for (int i = 0; i < m.nvert; i++)
+    for (int k = 0; k < 3; k++) verts4[4 * i + k] = m.hull_vert[3 * i + k];
   const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int k = 0; k < 9; k++) { xmat0[k] = I3[k]; xmat0[9 + k] = Rr[k]; if (nb == 3) xmat0[18 + k] = I3[k]; }
   // robot body origin with both slides at zero: body_pos - sum_j axis_j * qpos0_j  (xpos = body_pos + axis (q - q0))
@@ -240,6 +248,21 @@ __device__ __forceinline__ double impedance5(const double* c, double pos) {
 
 }  // namespace push
 
+// geometry of one geom for the shared narrowphase routines: pose from the tables / the block pose, no matrix product
+// for static and robot geoms
+__device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const PushInfo& fi, const push::Ws& s, int gi, Geom<float>& ge) {
+  ge.type = m.geom_type[gi]; ge.size = m.geom_size + 3 * gi;
+  ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
+  ge.verts4 = fi.verts4 + 4 * m.geom_vertadr[gi];
+  ge.pos = ld3(s.gpos + 3 * gi);
+  const double* gm = fi.gmatw + 9 * gi;
+  if (fi.gmove[gi] == 2) mulm(s.xmat + 9 * m.geom_body[gi], gm, ge.mat);
+  else {
+#pragma unroll
+    for (int k = 0; k < 9; k++) ge.mat[k] = gm[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- collision
 // Candidate pairs -> bounding-sphere + world-AABB cull (one pair per lane) -> narrowphase.  Contacts are appended to
 // the workspace in pair order (plane-box: corner order), exactly as the general kernel's collision() does.
@@ -313,8 +336,8 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
           ncon += nh;
         } else {
           Geom<float> A, B;
-          load_geom(m, w, m.pair_geom1[pk], A);
-          load_geom(m, w, m.pair_geom2[pk], B);
+          push_load_geom(m, fi, s, m.pair_geom1[pk], A);
+          push_load_geom(m, fi, s, m.pair_geom2[pk], B);
           if (func == NP_PLANE_CONVEX) {
             const V3<GT> n = mcol(A.mat, 2);
             const V3<GT> p = support_d(B, -n, g);
@@ -774,12 +797,8 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
             float wr[8];
 #pragma unroll
             for (int d = 0; d < 8; d++) wr[d] = 0.f;
-            if ((zones >> (8 + c)) & 1u) {
-              const push::F8 j = push::ld8(s.J + 8 * r);
-              const float Dv = s.Dr[r];
-#pragma unroll
-              for (int d = 0; d < 8; d++) wr[d] = Dv * j.v[d];
-            } else if ((zones >> c) & 1u) {
+            if (!((zones >> c) & 1u)) continue;   // quadratic-zone rows (W = D J) are applied directly in the Hessian loop
+            {
               const float* hc = s.Hc + 36 * c + 6 * ra;
 #pragma unroll 1
               for (int b = 0; b < 6; b++) {
@@ -797,8 +816,12 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
 #pragma unroll
           for (int j = 0; j < 8; j++) Hr[j] = 0.f;
           for (int r = sub; r < nr; r += SUBS) {
-            const float ji = s.J[8 * r + li];
-            const push::F8 wv = push::ld8(s.W + 8 * r);
+            const int c = r / 6;
+            const bool quad = (zones >> (8 + c)) & 1u, cone2 = (zones >> c) & 1u;
+            if (!quad && !cone2) continue;               // top zone: no force, no curvature
+            float ji = s.J[8 * r + li];
+            if (quad) ji *= s.Dr[r];
+            const push::F8 wv = push::ld8((quad ? s.J : s.W) + 8 * r);
 #pragma unroll
             for (int j = 0; j < 8; j++) Hr[j] += ji * wv.v[j];
           }
@@ -916,8 +939,9 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
                   const float Dm = lq[9];
                   const float NTv = N - mu_ * Tn;
                   const float N1 = lq[1];
-                  const float T1 = (lq[3] + alpha * lq[4]) / Tn;
-                  const float T2 = lq[4] / Tn - T1 * T1 / Tn;
+                  const float rT = 1.0f / Tn;
+                  const float T1 = (lq[3] + alpha * lq[4]) * rT;
+                  const float T2 = (lq[4] - T1 * T1) * rT;
                   l1 = Dm * NTv * (N1 - mu_ * T1);
                   l2 = Dm * ((N1 - mu_ * T1) * (N1 - mu_ * T1) - NTv * mu_ * T2);
                 }
