@@ -558,6 +558,7 @@ __device__ __noinline__ int hull_scan4(const float4* __restrict__ v, int n, floa
   float best = -FLT_MAX;
   int bi = 0x7fffffff;
   int i = g.lane;
+#pragma unroll 2
   for (; i + Grp::G < n; i += 2 * Grp::G) {
     const float4 a = v[i], b = v[i + Grp::G];
     const float va = a.x * lx + a.y * ly + a.z * lz, vb = b.x * lx + b.y * ly + b.z * lz;

@@ -139,9 +139,10 @@ int configure_fast(hsrb* h) {
   const int wpb_max = G == 16 ? 14 : 8;   // __launch_bounds__ of the kernel (hsrb_push.cuh)
   if (wpb > wpb_max) wpb = wpb_max;
   // shared memory: at most 227 KB per block
-  while (wpb > 1 && (size_t)h->fast_ws * (wpb * epw) > 227 * 1024) wpb--;
+  const size_t tail = push::shared_tail(mm);
+  while (wpb > 1 && (size_t)h->fast_ws * (wpb * epw) + tail > 227 * 1024) wpb--;
   h->fast_threads = 32 * wpb;
-  size_t smem = (size_t)h->fast_ws * (h->fast_threads / G);
+  size_t smem = (size_t)h->fast_ws * (h->fast_threads / G) + tail;
   CU(hsrb_push_prepare(G, h->fast.nv, smem, h->fast_threads, &h->fast_bps));
   if (h->fast_bps < 1) return fail(-3, "fast kernel does not fit on an SM (%zu bytes of shared memory)", smem);
   int epb = h->fast_threads / G;
@@ -166,7 +167,7 @@ int run(hsrb* h, KArgs& a, void* stream) {
     if (rc) return rc;
     a.ws_bytes = h->fast_ws;
     a.m.ncon_max = PUSH_MAXCON; a.m.nefc_max = 2 + PUSH_ROWS;
-    size_t smem = (size_t)h->fast_ws * (h->fast_threads / h->fast_lanes);
+    size_t smem = (size_t)h->fast_ws * (h->fast_threads / h->fast_lanes) + push::shared_tail(h->dm);
     CU(hsrb_push_launch(h->fast_lanes, h->fast.nv, a, h->fast, h->fast_grid, h->fast_threads, smem, (cudaStream_t)stream));
     h->launches++;
     return 0;

@@ -202,7 +202,11 @@ struct Ws {  // per-environment slice of shared memory
   float *con_dist, *con_pos, *con_frame;
   int *con_pair, *con_adr, *wi;
   float *J, *W, *Dr, *aref, *jar, *jv, *f, *Hc, *L;
+  const float* verts4;   // hull vertices of the model as float4, one copy per block (after the per-environment slices)
 };
+
+// bytes of the block-shared tail of dynamic shared memory (hull vertices as float4)
+__host__ __device__ inline size_t shared_tail(const ModelT<float>& m) { return (size_t)m.nvert * 16; }
 
 __host__ __device__ inline size_t carve(const ModelT<float>& m, Ws* w, unsigned char* base) {
   size_t off = 0;
@@ -253,7 +257,7 @@ __device__ __forceinline__ double impedance5(const double* c, double pos) {
 __device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const PushInfo& fi, const push::Ws& s, int gi, Geom<float>& ge) {
   ge.type = m.geom_type[gi]; ge.size = m.geom_size + 3 * gi;
   ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
-  ge.verts4 = fi.verts4 + 4 * m.geom_vertadr[gi];
+  ge.verts4 = s.verts4 + 4 * m.geom_vertadr[gi];   // block-shared copy in shared memory
   ge.pos = ld3(s.gpos + 3 * gi);
   const double* gm = fi.gmatw + 9 * gi;
   if (fi.gmove[gi] == 2) mulm(s.xmat + 9 * m.geom_body[gi], gm, ge.mat);
@@ -370,6 +374,14 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
   const int sub = g.lane >> 3;                // row stripe of this lane in dof-lane loops
   push::Ws s;
   push::carve(a.m, &s, smem + (size_t)gi * a.ws_bytes);
+  {
+    // block-shared copy of the hull vertices (128-bit shared loads in the support scan; generic global loads need a
+    // descriptor rebuilt from registers on every access when the warp is diverged)
+    float* v4 = reinterpret_cast<float*>(smem + (size_t)(blockDim.x / G) * a.ws_bytes);
+    for (int i = threadIdx.x; i < a.m.nvert * 4; i += blockDim.x) v4[i] = fi.verts4[i];
+    s.verts4 = v4;
+    __syncthreads();
+  }
   WS<float> w;                                // view for the shared narrowphase routines (hsr_core.h)
   w.xpos = s.xpos; w.xmat = s.xmat; w.gpos = s.gpos; w.gaabb = s.gaabb;
   w.con_dist = s.con_dist; w.con_pos = s.con_pos; w.con_frame = s.con_frame;
@@ -797,8 +809,12 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
             float wr[8];
 #pragma unroll
             for (int d = 0; d < 8; d++) wr[d] = 0.f;
-            if (!((zones >> c) & 1u)) continue;   // quadratic-zone rows (W = D J) are applied directly in the Hessian loop
-            {
+            if ((zones >> (8 + c)) & 1u) {
+              const push::F8 j = push::ld8(s.J + 8 * r);
+              const float Dv = s.Dr[r];
+#pragma unroll
+              for (int d = 0; d < 8; d++) wr[d] = Dv * j.v[d];
+            } else if ((zones >> c) & 1u) {
               const float* hc = s.Hc + 36 * c + 6 * ra;
 #pragma unroll 1
               for (int b = 0; b < 6; b++) {
@@ -816,12 +832,8 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
 #pragma unroll
           for (int j = 0; j < 8; j++) Hr[j] = 0.f;
           for (int r = sub; r < nr; r += SUBS) {
-            const int c = r / 6;
-            const bool quad = (zones >> (8 + c)) & 1u, cone2 = (zones >> c) & 1u;
-            if (!quad && !cone2) continue;               // top zone: no force, no curvature
-            float ji = s.J[8 * r + li];
-            if (quad) ji *= s.Dr[r];
-            const push::F8 wv = push::ld8((quad ? s.J : s.W) + 8 * r);
+            const float ji = s.J[8 * r + li];
+            const push::F8 wv = push::ld8(s.W + 8 * r);
 #pragma unroll
             for (int j = 0; j < 8; j++) Hr[j] += ji * wv.v[j];
           }

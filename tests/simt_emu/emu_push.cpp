@@ -52,7 +52,7 @@ extern "C" int emu_push_step(const void* blob, size_t bytes, int G, int threads,
   a.success = succ.data(); a.taken = tk.data(); a.bad = bad.data(); a.stats = stats.data();
   const int epb = threads / G;
   const int grid = (n + epb - 1) / epb;
-  const size_t smem = (size_t)a.ws_bytes * epb;
+  const size_t smem = (size_t)a.ws_bytes * epb + push::shared_tail(a.m);
   const int NV = m.nv;
 #define RUN(G_) { if (NV == 8) run<G_, 8>(a, fi, grid, threads, smem); else run<G_, 2>(a, fi, grid, threads, smem); }
   if (G == 8) RUN(8) else if (G == 16) RUN(16) else if (G == 32) RUN(32) else return -3;
