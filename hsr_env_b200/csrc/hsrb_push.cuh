@@ -309,7 +309,7 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
           hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
         }
       }
-      bits |= g.ballot(hit) << k0;
+      bits |= ((__ballot_sync(0xffffffffu, hit) >> g.shift) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))) << k0;   // full-warp vote, own group's bits
     }
     // ---- queue the convex-convex candidates of this environment (pair order) for the block's warps
     if (g.lane == 0) {
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
     bool success = false;
     bool finished = !valid || a.nsub <= 0;   // results written (or nothing to write)
     int taken = 0;
-    g.sync();
+    __syncwarp();
     if (valid && a.nsub <= 0) {
       // no substeps requested: the observation is the current state
       float* st = a.state + (size_t)env * a.S;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
           }
         }
       }
-      g.sync();
+      __syncwarp();
       HSR_PHASE(s, g, PH_KIN);
       // ---------------------------------------------------------------- active joint limits (redundant in every lane)
       float lim_sg[2], lim_D[2], lim_aref[2];
@@ -702,25 +702,41 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       int nefc_true = nlimit;  // MuJoCo's nefc: limit rows + condim rows per contact
       for (int c = 0; c < ncon; c++) nefc_true += m.pair_condim[s.con_pair[c]];
       sumcon += ncon; sumefc += nefc_true;
-      g.sync();
+      __syncwarp();
       HSR_PHASE(s, g, PH_ROWS);
 
       // ---------------------------------------------------------------- Newton solver (B.7)
+      // Warp-uniform control flow: every lane of the warp executes every statement of the solver; which environment
+      // is still iterating only decides what is committed (x, the rows, counters).  The groups of a warp therefore
+      // stay converged (a partial-mask __syncwarp / shuffle splits the warp into separately issued groups: the
+      // previous version ran this section at 8-16 active threads per instruction), synchronisation is the
+      // full-warp __syncwarp(), and reductions / broadcasts inside a group are full-mask shuffles whose partners stay
+      // inside the group (xor offsets below G, width-G segments).
       float x[8], qfc[8];  // qacc (replicated), J^T f (replicated after the solve)
 #pragma unroll
       for (int i = 0; i < 8; i++) { x[i] = 0.f; qfc[i] = 0.f; }
       int it = 0, ls_used = 0;
       int zone = 0;
       float cN = 0.f, cT = 0.f;
+      auto gsum = [&](float v) -> float {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        return v;
+      };
+      int nr_w = nr;   // longest row list among the warp's environments (uniform loop bounds)
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) { const int t = __shfl_xor_sync(FULL, nr_w, o); nr_w = t > nr_w ? t : nr_w; }
 
       // jar = J xx - aref for the contact rows (rows across lanes)
       auto rows_jar = [&](const float* xx) {
-        for (int r = g.lane; r < nr; r += G) {
-          const push::F8 j = push::ld8(s.J + 8 * r);
-          float acc = -s.aref[r];
+        for (int r = g.lane; r < nr_w; r += G) {
+          if (r < nr) {
+            const push::F8 j = push::ld8(s.J + 8 * r);
+            float acc = -s.aref[r];
 #pragma unroll
-          for (int d = 0; d < NV; d++) acc += j.v[d] * xx[d];
-          s.jar[r] = acc;
+            for (int d = 0; d < NV; d++) acc += j.v[d] * xx[d];
+            s.jar[r] = acc;
+          }
         }
       };
       // cone state of this lane's contact from its rows in s.jar: cost; full: zone, forces -> s.f
@@ -784,63 +800,68 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       };
 
       bool solving = nefc_true != 0;
+      bool finishing = false;   // converged by the improvement test: stop after the next gradient (forces of the final point)
       float cost = 0.f;
-      if (!solving) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) x[i] = as[i];
-      } else {
+      {
         // warm start: the cheaper of qacc_smooth / qacc_warmstart (ties -> warm start); evaluated in that order so
         // that s.jar already holds the rows of the usual winner
         rows_jar(as);
-        g.sync();
-        const float cs = g.sum(cone(false)) + gauss_of(as) + limit_cost(as);
-        g.sync();
+        __syncwarp();
+        const float cs = gsum(cone(false)) + gauss_of(as) + limit_cost(as);
+        __syncwarp();
         rows_jar(warm);
-        g.sync();
-        const float cw = g.sum(cone(false)) + gauss_of(warm) + limit_cost(warm);
-        const bool use_warm = cw <= cs;
+        __syncwarp();
+        const float cw = gsum(cone(false)) + gauss_of(warm) + limit_cost(warm);
+        const bool use_warm = cw <= cs && solving;   // no constraint rows: qacc = qacc_smooth
 #pragma unroll
         for (int i = 0; i < NV; i++) x[i] = use_warm ? warm[i] : as[i];
-        if (!use_warm) {
-          g.sync();
-          rows_jar(x);
-          g.sync();
-        }
-        cost = g.sum(cone(true)) + gauss_of(x) + limit_cost(x);
-        g.sync();
-      }
-      // Newton iterations: the loop is voted on by the whole warp so that its groups stay in step
-      while (__any_sync(FULL, solving)) {
-        if (solving) {
-          bool stop = false;
-          float srch[8], sn = 0.f, dec = 0.f, alpha = 0.f, gtol = 0.f;
+        __syncwarp();
+        if (__any_sync(FULL, !use_warm)) {
+          for (int r = g.lane; r < nr_w; r += G) {
+            if (r < nr && !use_warm) {
+              const push::F8 j = push::ld8(s.J + 8 * r);
+              float acc = -s.aref[r];
 #pragma unroll
-          for (int i = 0; i < 8; i++) srch[i] = 0.f;
-          // ---- gradient component of this lane's dof: M x - qfrc_smooth - J^T f
-          float myx = 0.f, myqs = 0.f, myM = 0.f;
-#pragma unroll
-          for (int i = 0; i < NV; i++) if (li == i) { myx = x[i]; myqs = qs[i]; myM = fi.Mdiag[i]; }
-          float qf = 0.f;
-          for (int r = sub; r < nr; r += SUBS) qf += s.J[8 * r + li] * s.f[r];
-#pragma unroll
-          for (int o = 8; o < G; o <<= 1) qf += __shfl_xor_sync(g.mask, qf, o);
-          bool lim_act[2];
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            lim_act[j] = false;
-            if (lim_sg[j] != 0.f) {
-              const float jr = lim_sg[j] * x[j] - lim_aref[j];
-              lim_act[j] = jr < 0;
-              if (lim_act[j] && li == j) qf += lim_sg[j] * (-lim_D[j] * jr);
+              for (int d = 0; d < NV; d++) acc += j.v[d] * x[d];
+              s.jar[r] = acc;
             }
           }
-          const float grad = (li < NV) ? myM * myx - myqs - qf : 0.f;
-          float gn = grad * grad;
+          __syncwarp();
+        }
+        cost = gsum(cone(true)) + gauss_of(x) + limit_cost(x);
+        __syncwarp();
+      }
+      // Newton iterations: the loop is voted on by the whole warp
+      while (__any_sync(FULL, solving)) {
+        bool stop = !solving;
+        // ---- gradient component of this lane's dof: M x - qfrc_smooth - J^T f
+        float myx = 0.f, myqs = 0.f, myM = 0.f;
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) gn += __shfl_xor_sync(g.mask, gn, o);
-          gn = sqrtf(gn);
-          if ((it > 0 && scale * gn < m.tolerance) || it >= m.iterations) stop = true;
-          if (!stop) {
+        for (int i = 0; i < NV; i++) if (li == i) { myx = x[i]; myqs = qs[i]; myM = fi.Mdiag[i]; }
+        float qf = 0.f;
+        for (int r = sub; r < nr_w; r += SUBS) if (r < nr) qf += s.J[8 * r + li] * s.f[r];
+#pragma unroll
+        for (int o = 8; o < G; o <<= 1) qf += __shfl_xor_sync(FULL, qf, o);
+        bool lim_act[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          lim_act[j] = false;
+          if (lim_sg[j] != 0.f) {
+            const float jr = lim_sg[j] * x[j] - lim_aref[j];
+            lim_act[j] = jr < 0;
+            if (lim_act[j] && li == j) qf += lim_sg[j] * (-lim_D[j] * jr);
+          }
+        }
+        const float grad = (li < NV) ? myM * myx - myqs - qf : 0.f;
+        float gn = grad * grad;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) gn += __shfl_xor_sync(FULL, gn, o);
+        gn = sqrtf(gn);
+        if (finishing || (it > 0 && scale * gn < m.tolerance) || it >= m.iterations) stop = true;
+        float qfg[8];   // qfrc_constraint of the current point, replicated (committed when this environment stops)
+#pragma unroll
+        for (int i = 0; i < 8; i++) qfg[i] = (i < NV) ? __shfl_sync(FULL, qf, i, G) : 0.f;
+        if (__any_sync(FULL, !stop)) {
           // ---- W rows (rows across lanes): zone 1 -> D J, zone 2 -> cone Hessian block times the contact's rows
           if (zone == 2) {
             float* hc = s.Hc + 36 * g.lane;
@@ -865,45 +886,51 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
                 hc[6 * aa + b] = (aa < dim && b < dim) ? Dm * scl[aa] * h * scl[b] : 0.f;
               }
           }
-          const unsigned zones = g.ballot(zone == 2) | (g.ballot(zone == 1) << 8);  // bit c: cone, bit 8+c: quadratic
-          g.sync();
-          for (int r = g.lane; r < nr; r += G) {
-            const int c = r / 6, ra = r - 6 * c;
-            float wr[8];
+          // zone bits of this group's contacts: bit c cone, bit 8+c quadratic
+          const unsigned zb2 = (__ballot_sync(FULL, zone == 2) >> g.shift) & 0xffu, zb1 = (__ballot_sync(FULL, zone == 1) >> g.shift) & 0xffu;
+          const unsigned zones = zb2 | (zb1 << 8);
+          __syncwarp();
+          for (int r = g.lane; r < nr_w; r += G) {
+            if (r < nr) {
+              const int c = r / 6, ra = r - 6 * c;
+              float wr[8];
 #pragma unroll
-            for (int d = 0; d < 8; d++) wr[d] = 0.f;
-            if ((zones >> (8 + c)) & 1u) {
-              const push::F8 j = push::ld8(s.J + 8 * r);
-              const float Dv = s.Dr[r];
+              for (int d = 0; d < 8; d++) wr[d] = 0.f;
+              if ((zones >> (8 + c)) & 1u) {
+                const push::F8 j = push::ld8(s.J + 8 * r);
+                const float Dv = s.Dr[r];
 #pragma unroll
-              for (int d = 0; d < 8; d++) wr[d] = Dv * j.v[d];
-            } else if ((zones >> c) & 1u) {
-              const float* hc = s.Hc + 36 * c + 6 * ra;
+                for (int d = 0; d < 8; d++) wr[d] = Dv * j.v[d];
+              } else if ((zones >> c) & 1u) {
+                const float* hc = s.Hc + 36 * c + 6 * ra;
 #pragma unroll 1
-              for (int b = 0; b < 6; b++) {
-                const push::F8 j = push::ld8(s.J + 8 * (6 * c + b));
-                const float h = hc[b];
+                for (int b = 0; b < 6; b++) {
+                  const push::F8 j = push::ld8(s.J + 8 * (6 * c + b));
+                  const float h = hc[b];
 #pragma unroll
-                for (int d = 0; d < 8; d++) wr[d] += h * j.v[d];
+                  for (int d = 0; d < 8; d++) wr[d] += h * j.v[d];
+                }
               }
+              push::st8(s.W + 8 * r, wr);
             }
-            push::st8(s.W + 8 * r, wr);
           }
-          g.sync();
+          __syncwarp();
           // ---- Hessian row of this lane's dof: M + J^T W  (+ active limits on the diagonal)
           float Hr[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) Hr[j] = 0.f;
-          for (int r = sub; r < nr; r += SUBS) {
-            const float ji = s.J[8 * r + li];
-            const push::F8 wv = push::ld8(s.W + 8 * r);
+          for (int r = sub; r < nr_w; r += SUBS) {
+            if (r < nr) {
+              const float ji = s.J[8 * r + li];
+              const push::F8 wv = push::ld8(s.W + 8 * r);
 #pragma unroll
-            for (int j = 0; j < 8; j++) Hr[j] += ji * wv.v[j];
+              for (int j = 0; j < 8; j++) Hr[j] += ji * wv.v[j];
+            }
           }
 #pragma unroll
           for (int o = 8; o < G; o <<= 1)
 #pragma unroll
-            for (int j = 0; j < 8; j++) Hr[j] += __shfl_xor_sync(g.mask, Hr[j], o);
+            for (int j = 0; j < 8; j++) Hr[j] += __shfl_xor_sync(FULL, Hr[j], o);
 #pragma unroll
           for (int j = 0; j < 8; j++) if (li == j) {
             Hr[j] += (j < NV) ? fi.Mdiag[j] : 1.0f;
@@ -914,8 +941,8 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
           float inv_diag = 1.f;
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            float dkk = __shfl_sync(g.mask, Hr[k], k, G);
-            if (!(dkk > 1e-15f)) { dkk = 1e-15f; flags |= FLAG_CHOL; }
+            float dkk = __shfl_sync(FULL, Hr[k], k, G);
+            if (!(dkk > 1e-15f)) { dkk = 1e-15f; if (!stop) flags |= FLAG_CHOL; }
             const float lkk = sqrtf(dkk);
             const float inv = 1.0f / lkk;
             const float lik = (li == k) ? lkk : Hr[k] * inv;   // L[i][k] for i >= k
@@ -923,7 +950,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
             if (li == k) inv_diag = inv;
 #pragma unroll
             for (int j = k + 1; j < 8; j++) {
-              const float ljk = __shfl_sync(g.mask, lik, j, G);
+              const float ljk = __shfl_sync(FULL, lik, j, G);
               Hr[j] -= lik * ljk;                               // meaningful for i >= j
             }
           }
@@ -931,14 +958,14 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
           float acc = -grad, y = 0.f;
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            const float yk = __shfl_sync(g.mask, acc * inv_diag, k, G);
+            const float yk = __shfl_sync(FULL, acc * inv_diag, k, G);
             if (li == k) y = yk;
             acc -= Hr[k] * yk;                                  // meaningful for i > k
           }
           // ---- backward solve L^T s = y: column k of L gathered through shared memory
-          g.sync();
+          __syncwarp();
           if (sub == 0) push::st8(s.L + 8 * li, Hr);
-          g.sync();
+          __syncwarp();
           float Lc[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) Lc[i] = s.L[8 * i + li];   // L[i][li], meaningful for i >= li
@@ -946,34 +973,36 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
           float sv = 0.f;
 #pragma unroll
           for (int k = 7; k >= 0; k--) {
-            const float xk = __shfl_sync(g.mask, acc * inv_diag, k, G);
+            const float xk = __shfl_sync(FULL, acc * inv_diag, k, G);
             if (li == k) sv = xk;
             acc -= Lc[k] * xk;                                  // meaningful for li < k
           }
+          float srch[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) srch[i] = (i < NV) ? __shfl_sync(g.mask, sv, i, G) : 0.f;
+          for (int i = 0; i < 8; i++) srch[i] = (i < NV) ? __shfl_sync(FULL, sv, i, G) : 0.f;
+          float sn = 0.f, dec = 0.f;
           {
             float dd = (li < NV) ? -grad * sv : 0.f;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) dd += __shfl_xor_sync(g.mask, dd, o);
+            for (int o = 1; o < 8; o <<= 1) dd += __shfl_xor_sync(FULL, dd, o);
             dec = dd;
           }
 #pragma unroll
           for (int i = 0; i < NV; i++) sn += srch[i] * srch[i];
           sn = sqrtf(sn);
-          if (sn < 1e-15f) stop = true;
-          }  // !stop: search direction
-          if (!stop) {
+          if (!(sn >= 1e-15f)) stop = true;                     // also catches the garbage direction of a stopped group
           // ---- jv = J search (rows across lanes)
-          for (int r = g.lane; r < nr; r += G) {
-            const push::F8 j = push::ld8(s.J + 8 * r);
-            float accv = 0.f;
+          for (int r = g.lane; r < nr_w; r += G) {
+            if (r < nr) {
+              const push::F8 j = push::ld8(s.J + 8 * r);
+              float accv = 0.f;
 #pragma unroll
-            for (int d = 0; d < NV; d++) accv += j.v[d] * srch[d];
-            s.jv[r] = accv;
+              for (int d = 0; d < NV; d++) accv += j.v[d] * srch[d];
+              s.jv[r] = accv;
+            }
           }
-          g.sync();
-          gtol = m.tolerance * m.ls_tolerance * sn / scale;
+          __syncwarp();
+          const float gtol = m.tolerance * m.ls_tolerance * sn / scale;
           // ---- exact line search: root of the 1-D derivative (safeguarded Newton with bracketing)
           float q1 = 0.f, q2 = 0.f;
 #pragma unroll
@@ -1022,7 +1051,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
                 }
               }
             }
-            l1 = g.sum(l1); l2 = g.sum(l2);
+            l1 = gsum(l1); l2 = gsum(l2);
 #pragma unroll
             for (int j = 0; j < 2; j++) if (lim_sg[j] != 0.f) {
               const float xv = lim_sg[j] * srch[j];
@@ -1032,6 +1061,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
             d1 = l1 + q1 + 2 * alpha * q2;
             d2 = l2 + 2 * q2;
           };
+          float alpha = 0.f;
           {
             float d1, d2;
             ls_eval(0.f, d1, d2);
@@ -1039,60 +1069,58 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
             float lo = 0.f, hi = -1.f, dlo = d1, dhi = 0.f;
             const float rel = 3.4526698e-4f;  // sqrt(FLT_EPSILON)
             bool conv = fabsf(d1) < gtol;
+            bool searching = !stop && !conv;                    // this environment still refines its step
 #pragma unroll 1
-            for (int lit = 0; lit < m.ls_iterations && !conv; lit++) {
-              const float step = d2 > 1e-15f ? -d1 / d2 : (d1 < 0 ? 1.f : -1.f);
-              float nxt = alpha + step;
-              if (hi >= 0 && !(lo < nxt && nxt < hi)) nxt = 0.5f * (lo + hi);
-              if (nxt <= 0 && hi < 0) nxt = alpha * 0.5f;
-              if (nxt == alpha) break;
-              const bool tiny = fabsf(nxt - alpha) <= rel * fabsf(nxt);
-              alpha = nxt;
-              ls_eval(alpha, d1, d2);
-              nev++;
-              if (d1 < 0) { if (alpha > lo) { lo = alpha; dlo = d1; } }
-              else if (hi < 0 || alpha < hi) { hi = alpha; dhi = d1; }
-              conv = fabsf(d1) < gtol || tiny;
+            for (int lit = 0; lit < m.ls_iterations; lit++) {
+              float nxt = alpha;
+              bool tiny = false;
+              if (searching) {
+                const float step = d2 > 1e-15f ? -d1 / d2 : (d1 < 0 ? 1.f : -1.f);
+                nxt = alpha + step;
+                if (hi >= 0 && !(lo < nxt && nxt < hi)) nxt = 0.5f * (lo + hi);
+                if (nxt <= 0 && hi < 0) nxt = alpha * 0.5f;
+                if (nxt == alpha) searching = false;
+                tiny = fabsf(nxt - alpha) <= rel * fabsf(nxt);
+              }
+              if (!__any_sync(FULL, searching)) break;
+              float e1, e2;
+              ls_eval(searching ? nxt : alpha, e1, e2);
+              if (searching) {
+                alpha = nxt; d1 = e1; d2 = e2;
+                nev++;
+                if (d1 < 0) { if (alpha > lo) { lo = alpha; dlo = d1; } }
+                else if (hi < 0 || alpha < hi) { hi = alpha; dhi = d1; }
+                conv = fabsf(d1) < gtol || tiny;
+                if (conv) searching = false;
+              }
             }
-            ls_used += nev;
+            if (!stop) ls_used += nev;
             if (!conv) {
               if (hi >= 0 && (lo <= 0 || fabsf(dhi) < fabsf(dlo))) alpha = (lo > 0 || fabsf(dhi) < fabsf(dlo)) ? hi : 0.f;
               else alpha = lo;
             }
           }
           if (alpha == 0.f) stop = true;
-          }  // !stop: line search
           if (!stop) {
 #pragma unroll
-          for (int i = 0; i < NV; i++) x[i] += alpha * srch[i];
-          for (int r = g.lane; r < nr; r += G) s.jar[r] += alpha * s.jv[r];
-          g.sync();
-          const float old = cost;
-          cost = g.sum(cone(true)) + gauss_of(x) + limit_cost(x);
-          g.sync();
-          it++;
-          const float improvement = alpha < 2.f ? alpha * (1.f - 0.5f * alpha) * dec : old - cost;
-          if (scale * improvement < m.tolerance) {
-            // forces of the final point for qfrc_constraint
-            float qf2 = 0.f;
-            for (int r = sub; r < nr; r += SUBS) qf2 += s.J[8 * r + li] * s.f[r];
-#pragma unroll
-            for (int o = 8; o < G; o <<= 1) qf2 += __shfl_xor_sync(g.mask, qf2, o);
-#pragma unroll
-            for (int j = 0; j < 2; j++) if (lim_sg[j] != 0.f) {
-              const float jr = lim_sg[j] * x[j] - lim_aref[j];
-              if (jr < 0 && li == j) qf2 += lim_sg[j] * (-lim_D[j] * jr);
-            }
-            qf = qf2;
-            stop = true;
+            for (int i = 0; i < NV; i++) x[i] += alpha * srch[i];
           }
-          }  // !stop: update
-          if (stop) {
-            // qfrc_constraint of the final point, replicated for the integrator
-#pragma unroll
-            for (int i = 0; i < NV; i++) qfc[i] = __shfl_sync(g.mask, qf, i, G);
-            solving = false;
+          for (int r = g.lane; r < nr_w; r += G) if (r < nr && !stop) s.jar[r] += alpha * s.jv[r];
+          __syncwarp();
+          const float newcost = gsum(cone(true)) + gauss_of(x) + limit_cost(x);   // stopped groups: unchanged rows, same result
+          __syncwarp();
+          if (!stop) {
+            const float old = cost;
+            cost = newcost;
+            it++;
+            const float improvement = alpha < 2.f ? alpha * (1.f - 0.5f * alpha) * dec : old - cost;
+            if (scale * improvement < m.tolerance) finishing = true;   // the next pass computes J^T f of this point and stops
           }
+        }
+        if (solving && stop) {
+#pragma unroll
+          for (int i = 0; i < NV; i++) qfc[i] = qfg[i];
+          solving = false;
         }
       }
       __syncthreads();
@@ -1128,7 +1156,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         }
         quatnormalize(qpos + 5);
       }
-      g.sync();
+      __syncwarp();
       HSR_PHASE(s, g, PH_EULER);
       if (!finished) {
         taken++;
@@ -1168,6 +1196,6 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         }
       }
     }
-    g.sync();
+    __syncwarp();
   }
 }
