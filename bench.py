@@ -146,9 +146,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_envs = max(cores * 4, 32)
-    # warm-up + timed "steps": each step = one action for a bounded sample of n_envs environments
-    cpu_port_run(n_envs, max(1, min(args.warmup, 1)), cores)
+    n_envs = max(cores * 32, 256)
+    # warm-up + timed "steps": each step = one action for a bounded sample of n_envs environments (of the 4096)
+    cpu_port_run(n_envs, max(1, min(args.warmup, 2)), cores)
     acts, subs, secs, flops = cpu_port_run(n_envs, args.steps, cores, budget_s=120.0)
     value = acts / secs
     line = {
@@ -197,10 +197,17 @@ def run_gpu(args):
     taken_sum = torch.zeros((), dtype=torch.int64, device=dev)
     succ_sum = torch.zeros((), dtype=torch.int64, device=dev)
 
-    def one_step(k):
+    kstart = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kend = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def one_step(k, timed=None):
         nonlocal done
         env.reset(mask=done)
+        if timed is not None:
+            kstart[timed].record()   # the action kernel alone (torch's current stream = the launching stream)
         obs, reward, done, inf = env.step(actions[k])
+        if timed is not None:
+            kend[timed].record()
         return inf["substeps_taken"]
 
     for k in range(args.warmup):
@@ -215,13 +222,14 @@ def run_gpu(args):
         for k in range(args.steps):
             flush.fill_(k & 0xff)           # evict L2 between timed iterations (outside the event bracket)
             starts[k].record()
-            taken = one_step(args.warmup + k)
+            taken = one_step(args.warmup + k, timed=k)
             ends[k].record()
             taken_sum += taken.sum()
             succ_sum += done.sum()
         torch.cuda.synchronize(dev)
     D.barrier()
     secs = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
+    kernel_s = sum(s.elapsed_time(e) for s, e in zip(kstart, kend)) * 1e-3 / args.steps   # mean action-kernel launch
     st1 = env.stats()
     secs_max = D.max_over_ranks(secs, dev)
     sub_local = float(taken_sum.item())
@@ -257,8 +265,11 @@ def run_gpu(args):
     nq, nv, nu = env.nq, env.nv, env.nu
     # algorithmic HBM bytes per env-action: state in/out once per action
     b_alg = 4 * ((nq + 2 * nv + nu + 3 + 2) + (nq + 2 * nv + (nq + nv) + 4))
-    step_kernel_s = secs_max / args.steps  # reset + action kernels; the action kernel is > 99 % of it
-    achieved_gbs = b_alg * n / step_kernel_s / 1e9
+    achieved_gbs = b_alg * n / kernel_s / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "r01_traffic.json"
+    if tp.exists() and n == 4096 and info["kernel"] == "fast":
+        traffic = json.loads(tp.read_text())["dram_bytes_per_launch"]
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     clocks = clk.summary()
     fp32_peak_at_clock = fp32_peak * (clocks["sm_mhz"] / sm_max) if clocks.get("sm_mhz") else None
@@ -278,9 +289,12 @@ def run_gpu(args):
                 "d2h_bytes_per_step": d2h, "substeps_per_s": None},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": which,
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": which + " (burst copy figure)",
+                     "kernel": "hsrb_push_kernel" if info["kernel"] == "fast" else "hsrb_step_kernel",
+                     "kernel_ms_per_launch": 1e3 * kernel_s, "algorithmic_bytes_per_launch": b_alg * n,
                      "algorithmic_bytes_per_env_action": b_alg,
-                     "note": "state crosses HBM once per action; the binding ceiling is the FP32 pipe / latency, see fp32"},
+                     "note": "state crosses HBM once per action (312 B per env-action): this path is bound by the instruction "
+                             "stream of a warp (issue / fetch latency), not by HBM or the FP32 pipe; see fp32 and DESIGN.md 4.1"},
         "fp32": {"achieved_tflops": achieved_tf, "peak_tflops_at_max_clock": fp32_peak,
                  "peak_tflops_at_observed_clock": fp32_peak_at_clock,
                  "frac_of_max_clock_peak": achieved_tf / fp32_peak,
