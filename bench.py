@@ -190,6 +190,8 @@ def run_gpu(args):
     gen = torch.Generator(device=dev).manual_seed(args.seed + 1000 * rank)
     total = args.warmup + args.steps
     actions = [lo + (hi - lo) * torch.rand(n, env.nu, generator=gen, device=dev) for _ in range(total)]
+    if args.action_scale != 1.0:   # experiments only (e.g. 0 = the robot stands still: floor contacts only)
+        actions = [a * args.action_scale for a in actions]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     env.reset()
@@ -334,6 +336,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--action-scale", type=float, default=1.0, help="experiments: scale the sampled actions")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

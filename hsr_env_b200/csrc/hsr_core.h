@@ -477,13 +477,14 @@ HSR_HDC void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
 
 // ------------------------------------------------------------------------------------------------ B.3 collision
 template <typename T> struct Geom {
-  int type; const T* size; const T* verts; int nvert; V3<GT> pos; GT mat[9];
+  int type; T size[3]; const T* verts; int nvert; V3<GT> pos; GT mat[9];   // size by value: read on every support call
   const T* verts4 = nullptr;  // optional copy of the hull vertices with a stride of 4 (16-byte aligned): 128-bit loads
 };
 
 template <typename T>
 HSR_HD void load_geom(const ModelT<T>& m, const WS<T>& w, int gi, Geom<T>& ge) {
-  ge.type = m.geom_type[gi]; ge.size = m.geom_size + 3 * gi;
+  ge.type = m.geom_type[gi];
+  for (int k = 0; k < 3; k++) ge.size[k] = m.geom_size[3 * gi + k];
   ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
   ge.pos = ld3(w.gpos + 3 * gi);
   GT gm[9];
@@ -612,11 +613,29 @@ HSR_HD void mpr_support(const Geom<T>& g1, const Geom<T>& g2, V3<double> d, cons
 }
 
 // Minkowski Portal Refinement penetration query (libccd ccdMPRPenetration as used by mjc_Convex).
+//
+// `sep` (optional, 4 floats: direction + valid flag) caches a separating direction of the pair between calls: a
+// direction d with max <a - b, d> < 0 proves the shapes disjoint, so a later call first spends one support
+// evaluation on the cached direction and returns "no contact" if it still separates (same decision as the full
+// query, which can only end without contact for disjoint shapes); every exit of the query that has such a
+// direction in hand stores it.  Callers without temporal coherence pass nullptr.
 template <typename T, typename Grp>
 HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,
-                             V3<GT>& pdir_, V3<GT>& ppos_) {
+                             V3<GT>& pdir_, V3<GT>& ppos_, float* sep = nullptr) {
   typedef double W;
   auto sup = [&](V3<W> d) { Sup<W> s; mpr_support(g1, g2, d, g, s); return s; };
+  auto miss = [&](V3<W> d) {   // disjoint along d: remember the direction
+    if (sep && g.lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = 1.f; }
+    return false;
+  };
+  if (sep && sep[3] != 0.f) {
+    V3<W> dc = normalized(mk<W>((W)sep[0], (W)sep[1], (W)sep[2]));
+    Sup<W> sc = sup(dc);
+    W dtc = dot(sc.v, dc);
+    if (dtc < 0 && !is_zero(dtc)) return false;
+    g.sync();
+    if (g.lane == 0) sep[3] = 0.f;
+  }
   auto reach_tol = [&](const Sup<W>& v1, const Sup<W>& v2, const Sup<W>& v3, const Sup<W>& v4, V3<W> d) {
     W dv4 = dot(v4.v, d);
     W d1 = dv4 - dot(v1.v, d), d2 = dv4 - dot(v2.v, d), d3 = dv4 - dot(v3.v, d);
@@ -643,7 +662,7 @@ HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int m
   V3<W> d = normalized(-v0.v);
   v1 = sup(d);
   W dt = dot(v1.v, d);
-  if (is_zero(dt) || dt < 0) return false;
+  if (is_zero(dt) || dt < 0) return dt < 0 && !is_zero(dt) ? miss(d) : false;
   d = cross(v0.v, v1.v);
   if (is_zero(dot(d, d))) {
     if (fabs(v1.v.x) < eps && fabs(v1.v.y) < eps && fabs(v1.v.z) < eps) return false;
@@ -653,13 +672,13 @@ HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int m
   d = normalized(d);
   v2 = sup(d);
   dt = dot(v2.v, d);
-  if (is_zero(dt) || dt < 0) return false;
+  if (is_zero(dt) || dt < 0) return dt < 0 && !is_zero(dt) ? miss(d) : false;
   d = normalized(cross(v1.v - v0.v, v2.v - v0.v));
   if (dot(d, v0.v) > 0) { Sup<W> t = v1; v1 = v2; v2 = t; d = -d; }
   for (int guard = 0; guard < 64; guard++) {
     v3 = sup(d);
     dt = dot(v3.v, d);
-    if (is_zero(dt) || dt < 0) return false;
+    if (is_zero(dt) || dt < 0) return dt < 0 && !is_zero(dt) ? miss(d) : false;
     bool cont = false;
     dt = dot(cross(v1.v, v3.v), v0.v);
     if (dt < 0 && !is_zero(dt)) { v2 = v3; cont = true; }
@@ -677,7 +696,8 @@ HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int m
     if (is_zero(dt) || dt > 0) break;
     v4 = sup(d);
     dt = dot(v4.v, d);
-    if (!(is_zero(dt) || dt > 0) || reach_tol(v1, v2, v3, v4, d)) return false;
+    if (!(is_zero(dt) || dt > 0)) return miss(d);
+    if (reach_tol(v1, v2, v3, v4, d)) return false;
     expand(v0, v1, v2, v3, v4);
   }
   // find penetration
@@ -1313,11 +1333,15 @@ HSR_HDC void euler_lane0(const ModelT<T>& m, WS<T>& w) {
 // Algorithmic flop count of one substep: the stage formulas of SURVEY.md §8(d) evaluated with the substep's actual
 // contact / row / iteration / line-search counts (what bench.py's FP32 roofline numerator is made of).
 template <typename T>
-HSR_HDC int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls, int npflop) {
-  int nv = m.nv, nb = m.nbody - 1, nfree = m.nblock;
-  bool articulated = false;  // any joint other than world-attached slides / free joints => M varies with qpos
+HSR_HD bool model_articulated(const ModelT<T>& m) {  // any joint other than world-attached slides / free joints => M varies with qpos
+  bool articulated = false;
   for (int j = 0; j < m.njnt; j++)
     if (m.jnt_type[j] == JNT_HINGE || m.body_parent[m.jnt_body[j]] > 0) articulated = true;
+  return articulated;
+}
+template <typename T>
+HSR_HD int algorithmic_flops(const ModelT<T>& m, bool articulated, int nc, int ne, int it, int ls, int npflop) {
+  int nv = m.nv, nb = m.nbody - 1, nfree = m.nblock;
   int f = 100 * nb + 60 * m.ngeom;                                   // FK + geom frames
   if (articulated) f += 60 * nb + 20 * nv + nv * nv * nv / 3;          // CRB + factorisation
   f += 9 * m.npair + npflop;                                           // broadphase + narrowphase
@@ -1331,6 +1355,10 @@ HSR_HDC int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls
   }
   f += 6 * nv + 60 * nfree + 10;                                       // Euler, quaternion integration, goal test
   return f;
+}
+template <typename T>
+HSR_HDC int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls, int npflop) {
+  return algorithmic_flops(m, model_articulated(m), nc, ne, it, ls, npflop);
 }
 
 // mj_forward up to and including the constraint solve (sim.forward(), /root/reference/hsr/env.py:176)

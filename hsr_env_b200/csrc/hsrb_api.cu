@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -158,6 +159,7 @@ KArgs base_args(hsrb* h) {
   memset(&a, 0, sizeof(a));
   a.m = h->dm; a.cfg = h->cfg; a.n = h->n; a.S = h->S; a.ws_bytes = h->ws_bytes;
   a.seed = h->seed; a.env_off = h->env_off; a.state = h->d_state; a.episode = h->d_episode; a.stats = h->d_stats;
+  if (const char* o = getenv("HSRB_OPTS")) a.opts = (unsigned)strtoul(o, nullptr, 0);   // experiment switches
   return a;
 }
 

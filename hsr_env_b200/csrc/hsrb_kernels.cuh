@@ -26,6 +26,7 @@ struct KArgs {
   ModelT<float> m;
   EnvCfg<float> cfg;
   int n, S, nsub, mode;
+  unsigned opts;           // experiment switches (HSRB_OPTS): bit 0 = no separating-direction cache in the fast kernel
   unsigned ws_bytes;
   unsigned long long seed, env_off;
   float* state;            // [N,S]: qpos nq | qvel nv | qacc_warmstart nv | mocap 3

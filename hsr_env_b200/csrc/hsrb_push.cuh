@@ -27,6 +27,7 @@
 #define PUSH_MAXJOBS 128   // queue capacity per block and pair chunk; overflowing jobs run in their own group
 #define PUSH_ENVJOBS 8     // queued jobs per environment and pair chunk
 #define PUSH_ROWS (6 * PUSH_MAXCON)   // fixed stride of 6 rows per contact; rows >= condim are zero rows
+#define PUSH_SEPMAX 32     // candidate pairs with a cached separating direction (mpr_penetration's `sep`)
 
 // Model constants of this kernel family, filled on the host (push_fill_info) and passed by value as a kernel
 // parameter (uniform constant-bank reads); the per-geom / per-pair tables are device arrays.
@@ -203,6 +204,7 @@ struct Ws {  // per-environment slice of shared memory
   int *con_pair, *con_adr, *wi;
   float *J, *W, *Dr, *aref, *jar, *jv, *f, *Hc, *L;
   int* jq;               // queue ids of this environment's convex-convex jobs, in pair order
+  float* sep;            // [min(npair, PUSH_SEPMAX)][4] separating direction + valid flag of each candidate pair
   const float* verts4;   // hull vertices of the model as float4, one copy per block (after the per-environment slices)
 };
 
@@ -235,6 +237,7 @@ __host__ __device__ inline size_t carve(const ModelT<float>& m, Ws* w, unsigned 
   CARVE(con_pair, int, nc) CARVE(con_adr, int, nc) CARVE(wi, int, WI_COUNT)
   CARVE(J, float, nr * 8) CARVE(W, float, nr * 8) CARVE(Dr, float, nr) CARVE(aref, float, nr) CARVE(jar, float, nr)
   CARVE(jv, float, nr) CARVE(f, float, nr) CARVE(Hc, float, nc * 36) CARVE(L, float, 64) CARVE(jq, int, PUSH_ENVJOBS)
+  CARVE(sep, float, 4 * (m.npair < PUSH_SEPMAX ? m.npair : PUSH_SEPMAX))
 #undef CARVE
   return off;
 }
@@ -270,7 +273,9 @@ __device__ __forceinline__ double impedance5(const double* c, double pos) {
 // geometry of one geom for the shared narrowphase routines: pose from the tables / the block pose, no matrix product
 // for static and robot geoms
 __device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const PushInfo& fi, const push::Ws& s, int gi, Geom<float>& ge) {
-  ge.type = m.geom_type[gi]; ge.size = m.geom_size + 3 * gi;
+  ge.type = m.geom_type[gi];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ge.size[k] = m.geom_size[3 * gi + k];
   ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
   ge.verts4 = s.verts4 + 4 * m.geom_vertadr[gi];   // block-shared copy in shared memory
   ge.pos = ld3(s.gpos + 3 * gi);
@@ -287,7 +292,7 @@ __device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const Pus
 // the workspace in pair order (plane-box: corner order), exactly as the general kernel's collision() does.
 template <int G>
 __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInfo& fi, push::Ws& s, WS<float>& w,
-                                           const DevGrp<G>& g, const push::Blk& blk, unsigned char* smem, unsigned ws_bytes) {
+                                           const DevGrp<G>& g, const push::Blk& blk, unsigned char* smem, unsigned ws_bytes, unsigned opts) {
   int ncon = 0, nrow = 0, narrow = 0, npflop = 0;
   const int gi = threadIdx.x / G;
   for (int base = 0; base < m.npair; base += 32) {
@@ -348,7 +353,8 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
         push_load_geom(m, fi, so, m.pair_geom1[pk], A);
         push_load_geom(m, fi, so, m.pair_geom2[pk], B);
         GT depth = 0; V3<GT> dir = mk<GT>(0, 0, 1), pos = mk<GT>(0, 0, 0);
-        const bool hit = mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, gw, depth, dir, pos);
+        const bool hit = mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, gw, depth, dir, pos,
+                                         pk < PUSH_SEPMAX && !(opts & 1u) ? so.sep + 4 * pk : nullptr);
         if (gw.lane == 0) {
           double* r = blk.res + 8 * j;
           r[0] = hit ? 1.0 : 0.0; r[1] = depth; r[2] = dir.x; r[3] = dir.y; r[4] = dir.z; r[5] = pos.x; r[6] = pos.y; r[7] = pos.z;
@@ -415,7 +421,7 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
             box_box(m, w, g, ncon, nrow, pk, A, B);
           } else {
             GT depth; V3<GT> dir, pos;
-            if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+            if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos, pk < PUSH_SEPMAX && !(opts & 1u) ? s.sep + 4 * pk : nullptr))
               add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
           }
         }
@@ -490,6 +496,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       if (a.ctrl)
         for (int i = 0; i < fi.act_n; i++) ctrl[i] = a.ctrl[(size_t)env * m.nu + i];
       for (int i = g.lane; i < WI_COUNT; i += G) s.wi[i] = 0;
+      for (int i = g.lane; i < 4 * (m.npair < PUSH_SEPMAX ? m.npair : PUSH_SEPMAX); i += G) s.sep[i] = 0.f;   // no cached directions
       // constant part of the pose workspace: body orientations, static geoms, robot AABBs
       for (int i = g.lane; i < m.nbody * 9; i += G) s.xmat[i] = fi.xmat0[i];
       for (int i = g.lane; i < m.nbody * 3; i += G) s.xpos[i] = 0;
@@ -582,7 +589,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         }
       }
       // ---------------------------------------------------------------- collision (B.3)
-      int ncon = push_collision<G>(m, fi, s, w, g, blk, smem, a.ws_bytes);
+      int ncon = push_collision<G>(m, fi, s, w, g, blk, smem, a.ws_bytes, a.opts);
       __syncthreads();
       if (ncon > PUSH_MAXCON) ncon = PUSH_MAXCON;
       flags |= s.wi[WI_FLAGS];
@@ -1126,7 +1133,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       __syncthreads();
       HSR_PHASE(s, g, PH_SOLVE);
       n_iter += it; n_ls += ls_used;
-      kflop += algorithmic_flops(m, ncon, nefc_true, it, ls_used, s.wi[WI_NPFLOP]);
+      kflop += algorithmic_flops(m, false, ncon, nefc_true, it, ls_used, s.wi[WI_NPFLOP]);   // slides + free box: M is constant
 
       // ---------------------------------------------------------------- goal test on the poses of this forward pass
       bool reached = false;

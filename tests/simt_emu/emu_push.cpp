@@ -2,6 +2,7 @@
 // through the SIMT emulator (simt_emu.h) so that its logic can be checked against the oracle on a box without a GPU.
 // Build: see tests/simt_emu/build.py.  Never linked into the product.
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,7 @@ extern "C" int emu_push_step(const void* blob, size_t bytes, int G, int threads,
   a.m.ncon_max = PUSH_MAXCON; a.m.nefc_max = 2 + PUSH_ROWS;
   a.cfg.has_goal = has_goal; a.cfg.geofence = (float)geofence; a.cfg.qidx0 = 0; a.cfg.qidx1 = 2;
   a.n = n; a.S = S; a.nsub = nsub; a.mode = MODE_STEP;
+  if (const char* o = getenv("HSRB_OPTS")) a.opts = (unsigned)strtoul(o, nullptr, 0);
   a.ws_bytes = (unsigned)push::carve(a.m, nullptr, nullptr);
   a.state = state.data(); a.ctrl = c32.data(); a.obs = obs.data(); a.reward = reward.data(); a.done = done.data();
   a.success = succ.data(); a.taken = tk.data(); a.bad = bad.data(); a.stats = stats.data();

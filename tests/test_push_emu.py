@@ -76,3 +76,18 @@ def test_emulated_kernel_goal_flags_and_early_exit(models, ports, emu):
     assert same.mean() >= 0.9
     assert np.mean(out["taken"][same] == ref["taken"][same]) >= 0.9
     assert np.all(out["taken"][out["success"] == 0] == 20)
+
+
+def test_emulated_kernel_separating_direction_cache(models, ports, emu, monkeypatch):
+    """The cached separating direction of a candidate pair (mpr_penetration's `sep`) only shortens queries that end
+    without a contact: a 40-substep action gives the same trajectory with the cache switched off (HSRB_OPTS bit 0)."""
+    model, port = models["c2_push"], ports["c2_push"]
+    qpos, qvel, warm, ctrl = rollout_states(port, model, 32, seed=5, float32=True)
+    out = emu.step(model, qpos, qvel, warm, ctrl, nsub=40, G=8, threads=64)
+    monkeypatch.setenv("HSRB_OPTS", "1")
+    ref = emu.step(model, qpos, qvel, warm, ctrl, nsub=40, G=8, threads=64)
+    assert np.all(out["flags"] == 0) and np.all(ref["flags"] == 0)
+    assert int(ref["stats"][2]) == int(out["stats"][2]) > 40 * 32          # same narrowphase calls, some convex-convex
+    same = np.all(out["qpos"] == ref["qpos"], axis=1) & np.all(out["qvel"] == ref["qvel"], axis=1)
+    assert same.mean() >= 0.95, same.mean()                                 # bitwise except borderline touching pairs
+    assert rel_err(out["qpos"], ref["qpos"]).max() <= 1e-4
