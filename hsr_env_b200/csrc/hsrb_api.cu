@@ -129,6 +129,7 @@ int configure_fast(hsrb* h) {
   if (h->fast_configured) return 0;
   ModelT<float> mm = h->dm;
   h->fast_ws = (unsigned)push::carve(mm, nullptr, nullptr);
+  if (const char* o = getenv("HSRB_PUSH_PAD")) h->fast_ws += 16u * (unsigned)atoi(o);   // experiments: stride of the environment slices
   // lanes per environment: the caller's choice (hsrb_config) when it is one this kernel has, else 8
   const int G = (h->lanes_req == 8 || h->lanes_req == 16 || h->lanes_req == 32) ? h->lanes_req : 8;
   h->fast_lanes = G;
@@ -139,6 +140,7 @@ int configure_fast(hsrb* h) {
   if (wpb < 1) wpb = 1;
   const int wpb_max = G == 16 ? 14 : 8;   // __launch_bounds__ of the kernel (hsrb_push.cuh)
   if (wpb > wpb_max) wpb = wpb_max;
+  if (const char* o = getenv("HSRB_PUSH_WPB")) { int v = atoi(o); if (v >= 1 && v <= wpb_max) wpb = v; }   // experiments
   // shared memory: at most 227 KB per block
   const size_t tail = push::shared_tail(mm);
   while (wpb > 1 && (size_t)h->fast_ws * (wpb * epw) + tail > 227 * 1024) wpb--;

@@ -20,11 +20,13 @@
 #pragma once
 #include "hsrb_kernels.cuh"
 
+#ifndef PUSH_MAXCON
 #define PUSH_MAXCON 8
+#endif
 // Block-wide barriers separate the phases of a substep: every warp of the SM runs the same code region at the same time
 // (ncu: instruction-fetch stalls fell from 57 % to 7 % of the samples) and the convex-convex narrowphase jobs of all
 // the block's environments go through one block-shared queue served by whole warps.
-#define PUSH_MAXJOBS 128   // queue capacity per block and pair chunk; overflowing jobs run in their own group
+#define PUSH_MAXJOBS 96    // queue capacity per block and pair chunk; overflowing jobs run in their own group
 #define PUSH_ENVJOBS 8     // queued jobs per environment and pair chunk
 #define PUSH_ROWS (6 * PUSH_MAXCON)   // fixed stride of 6 rows per contact; rows >= condim are zero rows
 #define PUSH_SEPMAX 32     // candidate pairs with a cached separating direction (mpr_penetration's `sep`)
@@ -213,16 +215,33 @@ struct Blk {
   int* ctr;        // [0] jobs queued, [1] next job to serve
   int* jobs;       // [PUSH_MAXJOBS] (group << 16) | pair
   double* res;     // [PUSH_MAXJOBS][8] hit, depth, direction, position
+  unsigned char* tab;   // block-shared model tables (Tab)
 };
+// Block-shared copies of the model tables the substep reads (a few KB): with ~200 KB of the SM's 256 KB carved out
+// as shared memory the L1 is small and L2 is flushed between actions, so a table read from global memory costs an L2
+// round trip on the critical path of every substep.
+struct Tab {
+  const double *gbase, *gmatw, *pairc;
+  const float *ghalf, *geom_rbound, *geom_size, *pair_friction, *geom_mat, *geom_aabb;
+  const int *gmove, *geom_type, *geom_body, *geom_vertadr, *geom_vertnum, *pair_geom1, *pair_geom2, *pair_func, *pair_condim;
+};
+__host__ __device__ inline size_t tab_bytes(const ModelT<float>& m) {
+  const size_t ng = m.ngeom, np = m.npair;
+  size_t b = 8 * (ng * 3 + ng * 9 + np * 8);
+  b += 4 * (ng * 3 + ng + ng * 3 + np * 5 + ng * 9 + ng * 3);
+  b += 4 * (ng * 5 + np * 4);
+  return (b + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t shared_tail(const ModelT<float>& m) {
-  return (size_t)m.nvert * 16 + 16 + sizeof(int) * PUSH_MAXJOBS + sizeof(double) * 8 * PUSH_MAXJOBS;
+  return (size_t)m.nvert * 16 + 16 + sizeof(int) * PUSH_MAXJOBS + sizeof(double) * 8 * PUSH_MAXJOBS + tab_bytes(m);
 }
 __host__ __device__ inline void carve_tail(const ModelT<float>& m, unsigned char* tail, const float** verts4, Blk* b) {
   *verts4 = (const float*)tail;
   unsigned char* p = tail + (size_t)m.nvert * 16;
   b->ctr = (int*)p; p += 16;
   b->jobs = (int*)p; p += sizeof(int) * PUSH_MAXJOBS;
-  b->res = (double*)p;
+  b->res = (double*)p; p += sizeof(double) * 8 * PUSH_MAXJOBS;
+  b->tab = p;
 }
 
 __host__ __device__ inline size_t carve(const ModelT<float>& m, Ws* w, unsigned char* base) {
@@ -272,15 +291,15 @@ __device__ __forceinline__ double impedance5(const double* c, double pos) {
 
 // geometry of one geom for the shared narrowphase routines: pose from the tables / the block pose, no matrix product
 // for static and robot geoms
-__device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const PushInfo& fi, const push::Ws& s, int gi, Geom<float>& ge) {
-  ge.type = m.geom_type[gi];
+__device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const push::Tab& t, const push::Ws& s, int gi, Geom<float>& ge) {
+  ge.type = t.geom_type[gi];
 #pragma unroll
-  for (int k = 0; k < 3; k++) ge.size[k] = m.geom_size[3 * gi + k];
-  ge.verts = m.hull_vert + 3 * m.geom_vertadr[gi]; ge.nvert = m.geom_vertnum[gi];
-  ge.verts4 = s.verts4 + 4 * m.geom_vertadr[gi];   // block-shared copy in shared memory
+  for (int k = 0; k < 3; k++) ge.size[k] = t.geom_size[3 * gi + k];
+  ge.verts = m.hull_vert + 3 * t.geom_vertadr[gi]; ge.nvert = t.geom_vertnum[gi];
+  ge.verts4 = s.verts4 + 4 * t.geom_vertadr[gi];   // block-shared copy in shared memory
   ge.pos = ld3(s.gpos + 3 * gi);
-  const double* gm = fi.gmatw + 9 * gi;
-  if (fi.gmove[gi] == 2) mulm(s.xmat + 9 * m.geom_body[gi], gm, ge.mat);
+  const double* gm = t.gmatw + 9 * gi;
+  if (t.gmove[gi] == 2) mulm(s.xmat + 9 * t.geom_body[gi], gm, ge.mat);
   else {
 #pragma unroll
     for (int k = 0; k < 9; k++) ge.mat[k] = gm[k];
@@ -291,7 +310,7 @@ __device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const Pus
 // Candidate pairs -> bounding-sphere + world-AABB cull (one pair per lane) -> narrowphase.  Contacts are appended to
 // the workspace in pair order (plane-box: corner order), exactly as the general kernel's collision() does.
 template <int G>
-__device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInfo& fi, push::Ws& s, WS<float>& w,
+__device__ __noinline__ int push_collision(const ModelT<float>& m, const push::Tab& t, push::Ws& s, WS<float>& w,
                                            const DevGrp<G>& g, const push::Blk& blk, unsigned char* smem, unsigned ws_bytes, unsigned opts) {
   int ncon = 0, nrow = 0, narrow = 0, npflop = 0;
   const int gi = threadIdx.x / G;
@@ -302,13 +321,13 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
       const int k = base + k0 + g.lane;
       bool hit = false;
       if (k < m.npair) {
-        const int a = m.pair_geom1[k], b = m.pair_geom2[k];
+        const int a = t.pair_geom1[k], b = t.pair_geom2[k];
         const V3<float> dp = cvt<float>(ld3(s.gpos + 3 * b) - ld3(s.gpos + 3 * a));
-        if (m.geom_type[a] == GEOM_PLANE) {
-          const double* Ma = fi.gmatw + 9 * a;  // planes are static: world orientation is a table entry
-          hit = dot(dp, mk<float>((float)Ma[2], (float)Ma[5], (float)Ma[8])) <= m.geom_rbound[b];
+        if (t.geom_type[a] == GEOM_PLANE) {
+          const double* Ma = t.gmatw + 9 * a;  // planes are static: world orientation is a table entry
+          hit = dot(dp, mk<float>((float)Ma[2], (float)Ma[5], (float)Ma[8])) <= t.geom_rbound[b];
         } else {
-          const float rr = m.geom_rbound[a] + m.geom_rbound[b];
+          const float rr = t.geom_rbound[a] + t.geom_rbound[b];
           hit = dot(dp, dp) <= rr * rr;
           const float* ha = s.gaabb + 3 * a; const float* hb = s.gaabb + 3 * b;
           hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
@@ -323,7 +342,7 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
       while (bb) {
         const int l = __ffs((int)bb) - 1;
         bb &= bb - 1;
-        if (m.pair_func[base + l] != NP_CONVEX_CONVEX) continue;
+        if (t.pair_func[base + l] != NP_CONVEX_CONVEX) continue;
         if (nq < PUSH_ENVJOBS) {
           int j = atomicAdd(blk.ctr, 1);
           if (j < PUSH_MAXJOBS) blk.jobs[j] = (gi << 16) | (base + l); else j = -1;
@@ -350,8 +369,8 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
         push::carve(m, &so, smem + (size_t)(code >> 16) * ws_bytes);
         so.verts4 = s.verts4;
         Geom<float> A, B;
-        push_load_geom(m, fi, so, m.pair_geom1[pk], A);
-        push_load_geom(m, fi, so, m.pair_geom2[pk], B);
+        push_load_geom(m, t, so, t.pair_geom1[pk], A);
+        push_load_geom(m, t, so, t.pair_geom2[pk], B);
         GT depth = 0; V3<GT> dir = mk<GT>(0, 0, 1), pos = mk<GT>(0, 0, 0);
         const bool hit = mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, gw, depth, dir, pos,
                                          pk < PUSH_SEPMAX && !(opts & 1u) ? so.sep + 4 * pk : nullptr);
@@ -370,23 +389,23 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
         const int l = __ffs((int)bits) - 1;
         bits &= bits - 1;
         const int pk = base + l;
-        const int func = m.pair_func[pk];
+        const int func = t.pair_func[pk];
         narrow++;
         npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
         if (func == NP_PLANE_BOX) {
           // mjc_PlaneBox: one corner per lane; the first four penetrating corners (corner order) become contacts
-          const int ga = m.pair_geom1[pk], gb = m.pair_geom2[pk];
-          const double* Ma = fi.gmatw + 9 * ga;
+          const int ga = t.pair_geom1[pk], gb = t.pair_geom2[pk];
+          const double* Ma = t.gmatw + 9 * ga;
           const V3<GT> n = mk<GT>(Ma[2], Ma[5], Ma[8]);
           const V3<GT> pb = ld3(s.gpos + 3 * gb);
           const GT dist0 = dot(pb - ld3(s.gpos + 3 * ga), n);
           const int i = g.lane;
-          const float* sz = m.geom_size + 3 * gb;
+          const float* sz = t.geom_size + 3 * gb;
           const V3<GT> c = mk<GT>((i & 1) ? (GT)sz[0] : -(GT)sz[0], (i & 2) ? (GT)sz[1] : -(GT)sz[1], (i & 4) ? (GT)sz[2] : -(GT)sz[2]);
           // geom orientation in the world: table entry (static / robot geoms) or xmat(block) * geom_mat, applied to the
           // corner as matrix-vector products
-          V3<GT> vec = mulv(fi.gmatw + 9 * gb, c);
-          if (fi.gmove[gb] == 2) vec = mulv(s.xmat + 9 * m.geom_body[gb], vec);
+          V3<GT> vec = mulv(t.gmatw + 9 * gb, c);
+          if (t.gmove[gb] == 2) vec = mulv(s.xmat + 9 * t.geom_body[gb], vec);
           const GT ld = dot(n, vec);
           const bool pen = i < 8 && !(dist0 + ld > 0 || ld > 0);
           const unsigned pm = g.ballot(pen);
@@ -410,8 +429,8 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const PushInf
         } else {
           if (func == NP_CONVEX_CONVEX) qi++;   // did not fit the queue: refine here, with this group's lanes
           Geom<float> A, B;
-          push_load_geom(m, fi, s, m.pair_geom1[pk], A);
-          push_load_geom(m, fi, s, m.pair_geom2[pk], B);
+          push_load_geom(m, t, s, t.pair_geom1[pk], A);
+          push_load_geom(m, t, s, t.pair_geom2[pk], B);
           if (func == NP_PLANE_CONVEX) {
             const V3<GT> n = mcol(A.mat, 2);
             const V3<GT> p = support_d(B, -n, g);
@@ -457,6 +476,27 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
     float* v4 = reinterpret_cast<float*>(tail);
     for (int i = threadIdx.x; i < a.m.nvert * 4; i += blockDim.x) v4[i] = fi.verts4[i];
     if (threadIdx.x == 0) { blk.ctr[0] = 0; blk.ctr[1] = 0; }
+  }
+  push::Tab t;
+  {
+    // block-shared copies of the model tables (doubles first: 8-byte alignment)
+    unsigned char* p = blk.tab;
+    const int ng = a.m.ngeom, np = a.m.npair;
+#define TAB_COPY(field, type, src, n)                                                        \
+  {                                                                                          \
+    type* d_ = reinterpret_cast<type*>(p);                                                   \
+    for (int i = threadIdx.x; i < (n); i += blockDim.x) d_[i] = (src)[i];                    \
+    t.field = d_; p += sizeof(type) * (size_t)(n);                                           \
+  }
+    TAB_COPY(gbase, double, fi.gbase, ng * 3) TAB_COPY(gmatw, double, fi.gmatw, ng * 9) TAB_COPY(pairc, double, fi.pairc, np * 8)
+    TAB_COPY(ghalf, float, fi.ghalf, ng * 3) TAB_COPY(geom_rbound, float, a.m.geom_rbound, ng)
+    TAB_COPY(geom_size, float, a.m.geom_size, ng * 3) TAB_COPY(pair_friction, float, a.m.pair_friction, np * 5)
+    TAB_COPY(geom_mat, float, a.m.geom_mat, ng * 9) TAB_COPY(geom_aabb, float, a.m.geom_aabb, ng * 3)
+    TAB_COPY(gmove, int, fi.gmove, ng) TAB_COPY(geom_type, int, a.m.geom_type, ng) TAB_COPY(geom_body, int, a.m.geom_body, ng)
+    TAB_COPY(geom_vertadr, int, a.m.geom_vertadr, ng) TAB_COPY(geom_vertnum, int, a.m.geom_vertnum, ng)
+    TAB_COPY(pair_geom1, int, a.m.pair_geom1, np) TAB_COPY(pair_geom2, int, a.m.pair_geom2, np)
+    TAB_COPY(pair_func, int, a.m.pair_func, np) TAB_COPY(pair_condim, int, a.m.pair_condim, np)
+#undef TAB_COPY
     __syncthreads();
   }
   WS<float> w;                                // view for the shared narrowphase routines (hsr_core.h)
@@ -501,8 +541,8 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       for (int i = g.lane; i < m.nbody * 9; i += G) s.xmat[i] = fi.xmat0[i];
       for (int i = g.lane; i < m.nbody * 3; i += G) s.xpos[i] = 0;
       for (int i = g.lane; i < m.ngeom * 3; i += G) {
-        s.gpos[i] = fi.gbase[i];
-        s.gaabb[i] = fi.ghalf[i];
+        s.gpos[i] = t.gbase[i];
+        s.gaabb[i] = t.ghalf[i];
       }
     }
     int n_iter = 0, n_ls = 0, sumcon = 0, sumefc = 0, kflop = 0, flags = 0;
@@ -547,18 +587,18 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       {
         const GT q0 = (GT)qpos[0], q1 = (GT)qpos[1];
         for (int gg = g.lane; gg < m.ngeom; gg += G) {
-          const int mv = fi.gmove[gg];
+          const int mv = t.gmove[gg];
           if (mv == 1) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) s.gpos[3 * gg + k] = fi.gbase[3 * gg + k] + fi.axisd[0][k] * q0 + fi.axisd[1][k] * q1;
+            for (int k = 0; k < 3; k++) s.gpos[3 * gg + k] = t.gbase[3 * gg + k] + fi.axisd[0][k] * q0 + fi.axisd[1][k] * q1;
           } else if (mv == 2) {
-            const V3<GT> p = mk<GT>(xb[0], xb[1], xb[2]) + mulv(Rb, ld3(fi.gbase + 3 * gg));
+            const V3<GT> p = mk<GT>(xb[0], xb[1], xb[2]) + mulv(Rb, ld3(t.gbase + 3 * gg));
             st3(s.gpos + 3 * gg, p);
             float Rbf[9], Rg[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) Rbf[k] = (float)Rb[k];
-            mulm(Rbf, m.geom_mat + 9 * gg, Rg);
-            const float* h = m.geom_aabb + 3 * gg;
+            mulm(Rbf, t.geom_mat + 9 * gg, Rg);
+            const float* h = t.geom_aabb + 3 * gg;
 #pragma unroll
             for (int i = 0; i < 3; i++)
               s.gaabb[3 * gg + i] = fabsf(Rg[3 * i]) * h[0] + fabsf(Rg[3 * i + 1]) * h[1] + fabsf(Rg[3 * i + 2]) * h[2];
@@ -589,7 +629,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         }
       }
       // ---------------------------------------------------------------- collision (B.3)
-      int ncon = push_collision<G>(m, fi, s, w, g, blk, smem, a.ws_bytes, a.opts);
+      int ncon = push_collision<G>(m, t, s, w, g, blk, smem, a.ws_bytes, a.opts);
       __syncthreads();
       if (ncon > PUSH_MAXCON) ncon = PUSH_MAXCON;
       flags |= s.wi[WI_FLAGS];
@@ -637,22 +677,22 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       if (g.lane < ncon) {
         const int c = g.lane;
         const int pk = s.con_pair[c];
-        dim = m.pair_condim[pk];
-        const int g1 = m.pair_geom1[pk], g2 = m.pair_geom2[pk];
-        const int b1 = m.geom_body[g1], b2 = m.geom_body[g2];
+        dim = t.pair_condim[pk];
+        const int g1 = t.pair_geom1[pk], g2 = t.pair_geom2[pk];
+        const int b1 = t.geom_body[g1], b2 = t.geom_body[g2];
         const float sr = (float)(b2 == fi.robot_body) - (float)(b1 == fi.robot_body);
         const float sbk = (float)(b2 == fi.block_body) - (float)(b1 == fi.block_body);
         float fr[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) fr[k] = s.con_frame[9 * c + k];
 #pragma unroll
-        for (int k = 0; k < 5; k++) fri[k] = m.pair_friction[5 * pk + k];
+        for (int k = 0; k < 5; k++) fri[k] = t.pair_friction[5 * pk + k];
         float rel[3] = {0.f, 0.f, 0.f};
         if (HASB) {
 #pragma unroll
           for (int k = 0; k < 3; k++) rel[k] = (float)((GT)s.con_pos[3 * c + k] - xb[k]);
         }
-        const double* pc = fi.pairc + 8 * pk;
+        const double* pc = t.pairc + 8 * pk;
         const GT dist = (GT)s.con_dist[c];
         const GT imp = push::impedance5(pc + 3, dist);
         const GT R0 = fmax(GT(1e-15), (1 - imp) / imp * pc[2]);
@@ -707,7 +747,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         mu = dim > 1 ? (float)((GT)fri[0] * sqrt(R1 / R0)) : fri[0];
       }
       int nefc_true = nlimit;  // MuJoCo's nefc: limit rows + condim rows per contact
-      for (int c = 0; c < ncon; c++) nefc_true += m.pair_condim[s.con_pair[c]];
+      for (int c = 0; c < ncon; c++) nefc_true += t.pair_condim[s.con_pair[c]];
       sumcon += ncon; sumefc += nefc_true;
       __syncwarp();
       HSR_PHASE(s, g, PH_ROWS);

@@ -136,6 +136,8 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 
 namespace emu {
 

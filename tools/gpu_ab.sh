@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/ab_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/ab_pytest.log
 python bench.py --steps 10 --warmup 3 --no-cpu "$@" > gpurun_out/ab_bench.json 2> gpurun_out/ab.err
-HSRB_OPTS=1 python bench.py --steps 10 --warmup 3 --no-cpu "$@" > gpurun_out/ab_bench_opts1.json 2>> gpurun_out/ab.err
+HSRB_OPTS=${ABOPTS:-1} python bench.py --steps 10 --warmup 3 --no-cpu "$@" > gpurun_out/ab_bench_opts1.json 2>> gpurun_out/ab.err
 tail -3 gpurun_out/ab_pytest.log
 python - <<'PY'
 import json
