@@ -104,6 +104,25 @@ struct DevGrp {
     for (int o = G_ / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o);
     return x;
   }
+  // full warp, float keys: two warp reductions (redux.sync) on an order-preserving integer image of the key instead of
+  // five shuffle rounds; ties go to the lowest index like the butterfly below
+  __device__ __forceinline__ void argmax(float& v, int& i) const {
+    if (G_ == 32) {
+      const unsigned u = __float_as_uint(v);
+      const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      const unsigned best = __reduce_max_sync(0xffffffffu, key);
+      i = __reduce_min_sync(0xffffffffu, key == best ? i : 0x7fffffff);
+      const unsigned b = (best & 0x80000000u) ? (best & 0x7fffffffu) : ~best;
+      v = __uint_as_float(b);
+      return;
+    }
+#pragma unroll
+    for (int o = G_ / 2; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(mask, v, o);
+      int oi = __shfl_xor_sync(mask, i, o);
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+  }
   template <typename T> __device__ __forceinline__ void argmax(T& v, int& i) const {
 #pragma unroll
     for (int o = G_ / 2; o > 0; o >>= 1) {

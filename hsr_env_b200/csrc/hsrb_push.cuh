@@ -515,6 +515,14 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
   // A group without an environment (tail of the batch) or whose environment has finished its action keeps computing
   // on a copy; its results were written when it finished and nothing is stored afterwards.
   constexpr unsigned FULL = 0xffffffffu;
+#ifndef PUSH_UNROLL_ROWS
+#define PUSH_UNROLL_ROWS 4
+#endif
+#ifndef PUSH_UNROLL_W
+#define PUSH_UNROLL_W 6
+#endif
+  constexpr int UW = PUSH_UNROLL_W;           // unroll factor of the cone-Hessian row product
+  constexpr int UR = PUSH_UNROLL_ROWS;        // unroll factor of the per-dof row loops (gradient, Hessian)
   for (int env0 = blockIdx.x * epb; env0 < a.n; env0 += gridDim.x * epb) {
     const bool valid = env0 + gi < a.n;
     const int env = valid ? env0 + gi : a.n - 1;
@@ -695,8 +703,12 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         const double* pc = t.pairc + 8 * pk;
         const GT dist = (GT)s.con_dist[c];
         const GT imp = push::impedance5(pc + 3, dist);
+        // regularisers: R0 = (1 - d) / d * diagApprox on the normal row, R0 / impratio on the first friction row, scaled by
+        // (fri0 / fri_r)^2 on the others.  One double division for the impedance ratio; the per-row inverses D = 1 / R
+        // are formed in float from D0 (relative rounding 1e-7 on a solver weight).
         const GT R0 = fmax(GT(1e-15), (1 - imp) / imp * pc[2]);
-        const GT R1 = R0 / (GT)m.impratio;
+        const float D0 = (float)(GT(1) / R0);
+        const float D1 = D0 * m.impratio;
         float vel[6];
 #pragma unroll
         for (int r = 0; r < 6; r++) {
@@ -733,18 +745,16 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         for (int r = 0; r < 6; r++) {
           float ar = 0.f, Dv = 0.f;
           if (r < dim) {
-            GT R;
-            if (r == 0) { R = R0; ar = (float)(-pc[1] * (GT)vel[0] - pc[0] * imp * dist); }
+            if (r == 0) { Dv = D0; ar = (float)(-pc[1] * (GT)vel[0] - pc[0] * imp * dist); }
             else {
               ar = (float)(-pc[1] * (GT)vel[r]);
-              R = r == 1 ? R1 : R1 * (GT)fri[0] * (GT)fri[0] / ((GT)fri[r - 1] * (GT)fri[r - 1]);
+              Dv = r == 1 ? D1 : D1 * (fri[r - 1] * fri[r - 1]) / (fri[0] * fri[0]);
             }
-            Dv = (float)(GT(1) / R);
           }
           D[r] = Dv;
           s.Dr[6 * c + r] = Dv; s.aref[6 * c + r] = ar;
         }
-        mu = dim > 1 ? (float)((GT)fri[0] * sqrt(R1 / R0)) : fri[0];
+        mu = dim > 1 ? fri[0] * rsqrtf(m.impratio) : fri[0];   // fri0 * sqrt(R1 / R0)
       }
       int nefc_true = nlimit;  // MuJoCo's nefc: limit rows + condim rows per contact
       for (int c = 0; c < ncon; c++) nefc_true += t.pair_condim[s.con_pair[c]];
@@ -886,6 +896,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
 #pragma unroll
         for (int i = 0; i < NV; i++) if (li == i) { myx = x[i]; myqs = qs[i]; myM = fi.Mdiag[i]; }
         float qf = 0.f;
+#pragma unroll UR
         for (int r = sub; r < nr_w; r += SUBS) if (r < nr) qf += s.J[8 * r + li] * s.f[r];
 #pragma unroll
         for (int o = 8; o < G; o <<= 1) qf += __shfl_xor_sync(FULL, qf, o);
@@ -950,7 +961,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
                 for (int d = 0; d < 8; d++) wr[d] = Dv * j.v[d];
               } else if ((zones >> c) & 1u) {
                 const float* hc = s.Hc + 36 * c + 6 * ra;
-#pragma unroll 1
+#pragma unroll UW
                 for (int b = 0; b < 6; b++) {
                   const push::F8 j = push::ld8(s.J + 8 * (6 * c + b));
                   const float h = hc[b];
@@ -966,6 +977,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
           float Hr[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) Hr[j] = 0.f;
+#pragma unroll UR
           for (int r = sub; r < nr_w; r += SUBS) {
             if (r < nr) {
               const float ji = s.J[8 * r + li];

@@ -101,6 +101,14 @@ template <typename T>
 inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
   return __shfl_sync(mask, v, (emu::tl_lane ^ lanemask) & (width - 1), width);
 }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+  for (int o = 16; o > 0; o >>= 1) { unsigned t = __shfl_xor_sync(mask, v, o); v = t > v ? t : v; }
+  return v;
+}
+inline int __reduce_min_sync(unsigned mask, int v) {
+  for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(mask, v, o); v = t < v ? t : v; }
+  return v;
+}
 inline unsigned __ballot_sync(unsigned mask, bool p) {
   emu::Warp& w = *emu::tl_warp;
   emu::SpinBarrier& b = w.bar(mask);
@@ -136,6 +144,10 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned __float_as_uint(float f) { unsigned v; memcpy(&v, &f, 4); return v; }
+inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 
