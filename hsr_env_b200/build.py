@@ -15,6 +15,10 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libhsrb.so"
 TUS = ["hsrb_api.cu", "hsrb_push.cu", "hsrb_step_g4.cu", "hsrb_step_g8.cu", "hsrb_step_g16.cu", "hsrb_step_g32.cu"]
 HEADERS = ["hsr_core.h", "hsr_model.h", "hsrb_kernels.cuh", "hsrb_push.cuh", "../../include/hsrb.h"]
+# per-TU flags: the fast-path kernel uses the 2-ulp fp32 division / square root (MUFU.RCP / MUFU.RSQ sequences without
+# the IEEE fix-up path; measured +6 % substeps/s, one-step error vs the fp64 oracle unchanged at the 1e-7 level); the
+# general kernel and the reset / forward paths keep IEEE division.
+TU_FLAGS = {"hsrb_push.cu": ["--prec-div=false", "--prec-sqrt=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -35,7 +39,7 @@ def build(force: bool = False, verbose: bool = False, phase_clocks: bool = False
     jobs = []
     name = tag
     tag = ".prof" if phase_clocks else (f".{tag}" if tag else "")
-    flags = FLAGS + (["-DHSRB_PHASE_CLOCKS"] if phase_clocks else []) + [f"-D{d}" for d in defines]
+    flags = FLAGS + (["-DHSRB_PHASE_CLOCKS"] if phase_clocks else []) + [f"-D{d}" for d in defines] + os.environ.get("NVCC_EXTRA", "").split()
     lib = CSRC / "libhsrb_prof.so" if phase_clocks else (CSRC / f"libhsrb_{name}.so" if name else LIB)
     for tu in TUS:
         src = CSRC / tu
@@ -46,7 +50,7 @@ def build(force: bool = False, verbose: bool = False, phase_clocks: bool = False
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC, *flags, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *flags, *TU_FLAGS.get(src.name, []), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (CSRC / (src.stem + tag + ".ptxas.log")).write_text(r.stderr)
         if r.returncode != 0:

@@ -579,7 +579,15 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       GT xb[3] = {0, 0, 0}, Rb[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
       if (HASB) {
         GT qd[4] = {(GT)qpos[5], (GT)qpos[6], (GT)qpos[7], (GT)qpos[8]};
+#if defined(__CUDA_ARCH__)
+        {  // quatnormalize with one reciprocal square root instead of a double sqrt and a double division
+          const GT n2 = qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3];
+          if (n2 < GT(1e-30)) { qd[0] = 1; qd[1] = qd[2] = qd[3] = 0; }
+          else { const GT inv = rsqrt(n2); qd[0] *= inv; qd[1] *= inv; qd[2] *= inv; qd[3] *= inv; }
+        }
+#else
         quatnormalize(qd);
+#endif
 #pragma unroll
         for (int k = 0; k < 4; k++) qpos[5 + k] = (float)qd[k];  // MuJoCo normalises qpos in place
         quat2mat(qd, Rb);
@@ -1209,8 +1217,19 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
         const float ang = sqrtf(om0 * om0 + om1 * om1 + om2 * om2);
         quatnormalize(qpos + 5);
         if (ang * dt > 1e-15f) {
-          const float hh = 0.5f * ang * dt, sn_ = sinf(hh) / ang;
-          float dq[4] = {cosf(hh), sn_ * om0, sn_ * om1, sn_ * om2};
+          // rotation by ang * dt about omega: dq = [cos h, sin(h) / ang * omega], h = ang dt / 2.  Below h = 0.5 rad per
+          // substep (ang < 500 rad/s) the series of cos h and sin(h) / h are exact to 1e-9 and need neither the range
+          // reduction of sinf / cosf nor the division by ang.
+          const float hh = 0.5f * ang * dt;
+          float ch, sn_;
+          if (hh < 0.5f) {
+            const float h2 = hh * hh;
+            ch = 1.f + h2 * (-0.5f + h2 * (4.1666667e-2f + h2 * (-1.3888889e-3f + h2 * (2.4801587e-5f - h2 * 2.7557319e-7f))));
+            sn_ = 0.5f * dt * (1.f + h2 * (-1.6666667e-1f + h2 * (8.3333333e-3f + h2 * (-1.9841270e-4f + h2 * 2.7557319e-6f))));
+          } else {
+            ch = cosf(hh); sn_ = sinf(hh) / ang;
+          }
+          float dq[4] = {ch, sn_ * om0, sn_ * om1, sn_ * om2};
           quatmul(qpos + 5, dq, qpos + 5);
         }
         quatnormalize(qpos + 5);
