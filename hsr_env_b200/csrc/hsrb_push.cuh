@@ -29,6 +29,7 @@
 #define PUSH_MAXJOBS 96    // queue capacity per block and pair chunk; overflowing jobs run in their own group
 #define PUSH_ENVJOBS 8     // queued jobs per environment and pair chunk
 #define PUSH_ROWS (6 * PUSH_MAXCON)   // fixed stride of 6 rows per contact; rows >= condim are zero rows
+#define PUSH_PAIRC 12      // doubles per candidate pair in PushInfo::pairc
 #define PUSH_SEPMAX 32     // candidate pairs with a cached separating direction (mpr_penetration's `sep`)
 
 // Model constants of this kernel family, filled on the host (push_fill_info) and passed by value as a kernel
@@ -53,13 +54,13 @@ struct PushInfo {
   const double* gmatw;    // [ngeom][9] world orientation of static / robot geoms; block geoms: geom_mat (body frame)
   const float* ghalf;     // [ngeom][3] world AABB half extents of static / robot geoms
   const int* gmove;       // [ngeom] 0 static, 1 rides on the robot, 2 rides on the block
-  const double* pairc;    // [npair][8] k, b, diagApprox, solimp d0, dmax, width, mid, power (clamped as MuJoCo does)
+  const double* pairc;    // [npair][PUSH_PAIRC] k, b, diagApprox, solimp d0, dmax, width, mid, power (clamped as MuJoCo does), 1/width, 1/mid, 1/(1-mid)
   const double* xmat0;    // [nbody][9] compile-time body orientations (world, robot; the block's is overwritten)
   const float* verts4;    // [nvert][4] hull vertices padded to 16 bytes (128-bit loads in the support scan)
 };
 
 // Host-side table builder (also used by the emulated build).  Layout of `tab` (doubles):
-//   gbase ngeom*3 | gmatw ngeom*9 | pairc npair*8 | xmat0 nbody*9 | ghalf ngeom*3 (floats, padded) | gmove ngeom (ints, padded)
+//   gbase ngeom*3 | gmatw ngeom*9 | pairc npair*PUSH_PAIRC | xmat0 nbody*9 | ghalf ngeom*3 (floats, padded) | gmove ngeom (ints, padded)
 struct PushTables {
   std::vector<double> tab;
   size_t off_gbase, off_gmatw, off_pairc, off_xmat0, off_ghalf, off_gmove, off_verts4;
@@ -145,9 +146,9 @@ inline bool push_fill_info(const ModelT<float>& m, PushInfo& f, PushTables& t, c
   for (int k = 0; k < 3; k++) f.gravity[k] = m.gravity[k];
   // ---- tables
   const int ng = m.ngeom, np = m.npair, nb = m.nbody;
-  size_t nd = (size_t)ng * 3 + (size_t)ng * 9 + (size_t)np * 8 + (size_t)nb * 9;
+  size_t nd = (size_t)ng * 3 + (size_t)ng * 9 + (size_t)np * PUSH_PAIRC + (size_t)nb * 9;
   t.off_gbase = 0; t.off_gmatw = sizeof(double) * ng * 3; t.off_pairc = t.off_gmatw + sizeof(double) * ng * 9;
-  t.off_xmat0 = t.off_pairc + sizeof(double) * np * 8;
+  t.off_xmat0 = t.off_pairc + sizeof(double) * np * PUSH_PAIRC;
   t.off_ghalf = sizeof(double) * nd;
   size_t nhalf_d = ((size_t)ng * 3 * sizeof(float) + 7) / 8, nmove_d = ((size_t)ng * sizeof(int) + 7) / 8;
   t.off_gmove = t.off_ghalf + 8 * nhalf_d;
@@ -155,7 +156,7 @@ inline bool push_fill_info(const ModelT<float>& m, PushInfo& f, PushTables& t, c
   t.off_verts4 += (16 - t.off_verts4 % 16) % 16;
   const size_t nv4_d = ((size_t)m.nvert * 4 * sizeof(float) + 7) / 8 + 2;
   t.tab.assign(t.off_verts4 / 8 + nv4_d, 0.0);
-  double* gbase = t.tab.data(); double* gmatw = gbase + ng * 3; double* pairc = gmatw + ng * 9; double* xmat0 = pairc + np * 8;
+  double* gbase = t.tab.data(); double* gmatw = gbase + ng * 3; double* pairc = gmatw + ng * 9; double* xmat0 = pairc + np * PUSH_PAIRC;
   float* ghalf = (float*)((unsigned char*)t.tab.data() + t.off_ghalf);
   int* gmove = (int*)((unsigned char*)t.tab.data() + t.off_gmove);
   float* verts4 = (float*)((unsigned char*)t.tab.data() + t.off_verts4);
@@ -189,8 +190,9 @@ inline bool push_fill_info(const ModelT<float>& m, PushInfo& f, PushTables& t, c
     for (int i = 0; i < 3; i++) ghalf[3 * gi + i] = std::fabs(Rg[3 * i]) * h[0] + std::fabs(Rg[3 * i + 1]) * h[1] + std::fabs(Rg[3 * i + 2]) * h[2];
   }
   for (int pk = 0; pk < np; pk++) {
-    double* c = pairc + 8 * pk;
+    double* c = pairc + PUSH_PAIRC * pk;
     push_row_consts((double)m.timestep, m.pair_solref + 2 * pk, m.pair_solimp + 5 * pk, c + 0, c + 1, c + 3);
+    c[8] = 1.0 / c[5]; c[9] = 1.0 / c[6]; c[10] = 1.0 / (1.0 - c[6]); c[11] = 0.0;   // reciprocals for impedance5<true>
     c[2] = (double)(m.geom_invweight[m.pair_geom1[pk]] + m.geom_invweight[m.pair_geom2[pk]]);  // fp32 sum, as row setup does
   }
   why[0] = 0;
@@ -227,7 +229,7 @@ struct Tab {
 };
 __host__ __device__ inline size_t tab_bytes(const ModelT<float>& m) {
   const size_t ng = m.ngeom, np = m.npair;
-  size_t b = 8 * (ng * 3 + ng * 9 + np * 8);
+  size_t b = 8 * (ng * 3 + ng * 9 + np * PUSH_PAIRC);
   b += 4 * (ng * 3 + ng + ng * 3 + np * 5 + ng * 9 + ng * 3);
   b += 4 * (ng * 5 + np * 4);
   return (b + 15) & ~(size_t)15;
@@ -272,16 +274,18 @@ __device__ __forceinline__ void st8(float* p, const float* v) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-// impedance d(|pos|) with pre-clamped parameters c = {d0, dmax, width, mid, power}  (App. B.5)
+// impedance d(|pos|) with pre-clamped parameters c = {d0, dmax, width, mid, power}  (App. B.5); INV: c[5..7] hold
+// 1/width, 1/mid, 1/(1-mid) (the candidate-pair table), which takes three double divisions off every contact
+template <bool INV = false>
 __device__ __forceinline__ double impedance5(const double* c, double pos) {
   const double d0 = c[0], dmax = c[1], width = c[2], mid = c[3], power = c[4];
   if (d0 == dmax || width <= 1e-15) return 0.5 * (d0 + dmax);
-  const double x = fabs(pos) / width;
+  const double x = INV ? fabs(pos) * c[5] : fabs(pos) / width;
   if (x >= 1) return dmax;
   if (x == 0) return d0;
   double y;
   if (power == 1) y = x;
-  else if (power == 2) y = x <= mid ? (1.0 / mid) * (x * x) : 1.0 - (1.0 / (1.0 - mid)) * ((1.0 - x) * (1.0 - x));
+  else if (power == 2) y = x <= mid ? (INV ? c[6] : 1.0 / mid) * (x * x) : 1.0 - (INV ? c[7] : 1.0 / (1.0 - mid)) * ((1.0 - x) * (1.0 - x));
   else if (x <= mid) y = (1.0 / pow(mid, power - 1)) * pow(x, power);
   else y = 1.0 - (1.0 / pow(1 - mid, power - 1)) * pow(1 - x, power);
   return d0 + y * (dmax - d0);
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
     for (int i = threadIdx.x; i < (n); i += blockDim.x) d_[i] = (src)[i];                    \
     t.field = d_; p += sizeof(type) * (size_t)(n);                                           \
   }
-    TAB_COPY(gbase, double, fi.gbase, ng * 3) TAB_COPY(gmatw, double, fi.gmatw, ng * 9) TAB_COPY(pairc, double, fi.pairc, np * 8)
+    TAB_COPY(gbase, double, fi.gbase, ng * 3) TAB_COPY(gmatw, double, fi.gmatw, ng * 9) TAB_COPY(pairc, double, fi.pairc, np * PUSH_PAIRC)
     TAB_COPY(ghalf, float, fi.ghalf, ng * 3) TAB_COPY(geom_rbound, float, a.m.geom_rbound, ng)
     TAB_COPY(geom_size, float, a.m.geom_size, ng * 3) TAB_COPY(pair_friction, float, a.m.pair_friction, np * 5)
     TAB_COPY(geom_mat, float, a.m.geom_mat, ng * 9) TAB_COPY(geom_aabb, float, a.m.geom_aabb, ng * 3)
@@ -708,14 +712,13 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
 #pragma unroll
           for (int k = 0; k < 3; k++) rel[k] = (float)((GT)s.con_pos[3 * c + k] - xb[k]);
         }
-        const double* pc = t.pairc + 8 * pk;
+        const double* pc = t.pairc + PUSH_PAIRC * pk;
         const GT dist = (GT)s.con_dist[c];
-        const GT imp = push::impedance5(pc + 3, dist);
+        const GT imp = push::impedance5<true>(pc + 3, dist);
         // regularisers: R0 = (1 - d) / d * diagApprox on the normal row, R0 / impratio on the first friction row, scaled by
         // (fri0 / fri_r)^2 on the others.  One double division for the impedance ratio; the per-row inverses D = 1 / R
         // are formed in float from D0 (relative rounding 1e-7 on a solver weight).
-        const GT R0 = fmax(GT(1e-15), (1 - imp) / imp * pc[2]);
-        const float D0 = (float)(GT(1) / R0);
+        const float D0 = (float)fmin(GT(1e15), imp / ((1 - imp) * pc[2]));   // 1 / max(1e-15, R0)
         const float D1 = D0 * m.impratio;
         float vel[6];
 #pragma unroll
@@ -1100,7 +1103,8 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
               const float mu_ = lq[8];
               const float N = lq[0] + alpha * lq[1];
               const float tsq = lq[2] + alpha * (2 * lq[3] + alpha * lq[4]);
-              const float Tn = tsq > 0 ? sqrtf(tsq) : 0.f;
+              const float rT = tsq > 0 ? rsqrtf(tsq) : 0.f;     // 1 / T (used in the cone zone only, where T > 0)
+            const float Tn = tsq * rT;
               bool top = (N >= mu_ * Tn) || (Tn <= 0 && N >= 0);
               bool bottom = (mu_ * N + Tn <= 0) || (Tn <= 0 && N < 0);
               if (lq[9] < 0) { top = !(N < 0); bottom = N < 0; }
@@ -1110,8 +1114,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
                   const float Dm = lq[9];
                   const float NTv = N - mu_ * Tn;
                   const float N1 = lq[1];
-                  const float rT = 1.0f / Tn;
-                  const float T1 = (lq[3] + alpha * lq[4]) * rT;
+                    const float T1 = (lq[3] + alpha * lq[4]) * rT;
                   const float T2 = (lq[4] - T1 * T1) * rT;
                   l1 = Dm * NTv * (N1 - mu_ * T1);
                   l2 = Dm * ((N1 - mu_ * T1) * (N1 - mu_ * T1) - NTv * mu_ * T2);
