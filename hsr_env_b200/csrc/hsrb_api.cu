@@ -99,8 +99,17 @@ cudaError_t launch(int G, const KArgs& a, int grid, size_t smem, cudaStream_t s)
 int configure(hsrb* h) {
   if (h->configured) return 0;
   h->ws_bytes = (unsigned)ws_carve<float>(h->dm, nullptr, nullptr);
+  // lanes per environment: the widest layout that holds every environment in one wave; if none does, shared memory
+  // decides how many environments an SM holds (one warp per block, 32/G workspaces per block), and among the layouts
+  // within 10 % of the best residency the narrowest one wins: the single-lane stages (kinematics, bias forces, Euler)
+  // then run for 32/G environments at once.  Measured on B200 (tools/sweep_lanes.py): C3 (nv = 13, 16384 envs)
+  // G = 8: 3.5 M substeps/s against 2.6 M (G = 4, one block per SM) and 1.1 M (G = 32); C5 (nv = 26): G = 32 0.53 M
+  // against 0.29 M (G = 16)
   int cands[4] = {32, 16, 8, 4};
   int best = 0;
+  long long res[4] = {0, 0, 0, 0};
+  int bpsv[4] = {0, 0, 0, 0};
+  long long resmax = 0;
   for (int k = 0; k < 4; k++) {
     int G = cands[k];
     if (h->lanes_req && G != h->lanes_req) continue;
@@ -108,10 +117,14 @@ int configure(hsrb* h) {
     if (smem > 227 * 1024) continue;
     int bps = 0;
     if (prepare(G, smem, &bps) != cudaSuccess || bps <= 0) { cudaGetLastError(); continue; }
-    long long resident = (long long)bps * h->num_sm * (32 / G);
-    best = G; h->blocks_per_sm = bps;
-    if (resident >= h->n) break;  // first (widest) G that holds every environment in one wave
+    bpsv[k] = bps;
+    res[k] = (long long)bps * h->num_sm * (32 / G);
+    if (res[k] > resmax) resmax = res[k];
   }
+  for (int k = 0; k < 4 && !best; k++)
+    if (res[k] >= h->n) { best = cands[k]; h->blocks_per_sm = bpsv[k]; }
+  for (int k = 3; k >= 0 && !best; k--)
+    if (res[k] > 0 && res[k] * 10 >= resmax * 9) { best = cands[k]; h->blocks_per_sm = bpsv[k]; }
   if (!best) return fail(-3, "no launch configuration fits: workspace %u bytes per environment", h->ws_bytes);
   h->lanes = best;
   size_t smem = (size_t)h->ws_bytes * (32 / best);
