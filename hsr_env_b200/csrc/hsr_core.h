@@ -107,6 +107,7 @@ struct DevGrp {
   // full warp, float keys: two warp reductions (redux.sync) on an order-preserving integer image of the key instead of
   // five shuffle rounds; ties go to the lowest index like the butterfly below
   __device__ __forceinline__ void argmax(float& v, int& i) const {
+#ifndef HSR_NO_REDUX
     if (G_ == 32) {
       const unsigned u = __float_as_uint(v);
       const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -116,6 +117,7 @@ struct DevGrp {
       v = __uint_as_float(b);
       return;
     }
+#endif
 #pragma unroll
     for (int o = G_ / 2; o > 0; o >>= 1) {
       float ov = __shfl_xor_sync(mask, v, o);

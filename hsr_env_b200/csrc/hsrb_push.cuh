@@ -583,15 +583,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
       GT xb[3] = {0, 0, 0}, Rb[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
       if (HASB) {
         GT qd[4] = {(GT)qpos[5], (GT)qpos[6], (GT)qpos[7], (GT)qpos[8]};
-#if defined(__CUDA_ARCH__)
-        {  // quatnormalize with one reciprocal square root instead of a double sqrt and a double division
-          const GT n2 = qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3];
-          if (n2 < GT(1e-30)) { qd[0] = 1; qd[1] = qd[2] = qd[3] = 0; }
-          else { const GT inv = rsqrt(n2); qd[0] *= inv; qd[1] *= inv; qd[2] *= inv; qd[3] *= inv; }
-        }
-#else
-        quatnormalize(qd);
-#endif
+        quatnormalize(qd);   // same rounding as the oracle: the narrowphase decisions downstream are discontinuous in the pose
 #pragma unroll
         for (int k = 0; k < 4; k++) qpos[5 + k] = (float)qd[k];  // MuJoCo normalises qpos in place
         quat2mat(qd, Rb);

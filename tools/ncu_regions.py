@@ -17,7 +17,7 @@ for name,pat in markers:
 push.sort()
 pst=[a for a,_ in push]
 core_src=open('hsr_env_b200/csrc/hsr_core.h').read().splitlines()
-cm=[('groups','struct HostGrp'),('vec3/quat','template <typename T> struct V3'),('workspace','struct WS {'),('kinematics','HSR_HDC void kinematics_lane0'),('geom util','template <typename T> struct Geom'),('make_frame','HSR_HD void make_frame'),('add_contact','HSR_HDC void add_contact'),('mpr:tri','HSR_HD T origin_tri_dist2'),('hull_scan4','__device__ __noinline__ int hull_scan4'),('support_d','HSR_HD V3<double> support_d'),('mpr_support','HSR_HD void mpr_support'),('mpr','HSR_HDN bool mpr_penetration'),('box_box','HSR_HDN void box_box'),('narrow_pair','HSR_HD void narrow_pair'),('impedance','HSR_HD GT impedance'),('solver','HSR_HD int cone_zone'),('flops','HSR_HDC int algorithmic_flops'),('forward','HSR_HDC void forward')]
+cm=[('groups','struct HostGrp'),('vec3/quat','template <typename T> struct V3'),('workspace','struct WS {'),('kinematics','HSR_HDC void kinematics_lane0'),('geom util','template <typename T> struct Geom'),('make_frame','HSR_HD void make_frame'),('add_contact','HSR_HDC void add_contact'),('mpr:tri','HSR_HD T origin_tri_dist2'),('hull_scan4','__device__ __noinline__ int hull_scan4'),('support_d','HSR_HD V3<double> support_d'),('mpr_support','HSR_HD void mpr_support'),('mpr','HSR_HDN bool mpr_penetration'),('box_box','HSR_HDN void box_box'),('narrow_pair','HSR_HD void narrow_pair'),('impedance','HSR_HD GT impedance'),('solver','HSR_HD int cone_zone'),('flops (+ wait at the block barrier after the solver)','HSR_HD bool model_articulated'),('forward','HSR_HDC void forward')]
 core=[]
 for name,pat in cm:
     for i,l in enumerate(core_src):
