@@ -206,7 +206,8 @@ struct Ws {  // per-environment slice of shared memory
   float* gaabb;
   float *con_dist, *con_pos, *con_frame;
   int *con_pair, *con_adr, *wi;
-  float *J, *W, *Dr, *aref, *jar, *jv, *f, *Hc, *L;
+  float *J, *Dr, *aref, *jar, *jv, *f, *L;
+  float* hq;             // rank-1 Hessian terms: p, q of the cone contacts [MAXCON][16], their weights [MAXCON][2], row weights [ROWS]
   int* jq;               // queue ids of this environment's convex-convex jobs, in pair order
   float* sep;            // [min(npair, PUSH_SEPMAX)][4] separating direction + valid flag of each candidate pair
   const float* verts4;   // hull vertices of the model as float4, one copy per block (after the per-environment slices)
@@ -256,8 +257,8 @@ __host__ __device__ inline size_t carve(const ModelT<float>& m, Ws* w, unsigned 
   CARVE(gaabb, float, m.ngeom * 3)
   CARVE(con_dist, float, nc) CARVE(con_pos, float, nc * 3) CARVE(con_frame, float, nc * 9)
   CARVE(con_pair, int, nc) CARVE(con_adr, int, nc) CARVE(wi, int, WI_COUNT)
-  CARVE(J, float, nr * 8) CARVE(W, float, nr * 8) CARVE(Dr, float, nr) CARVE(aref, float, nr) CARVE(jar, float, nr)
-  CARVE(jv, float, nr) CARVE(f, float, nr) CARVE(Hc, float, nc * 36) CARVE(L, float, 64) CARVE(jq, int, PUSH_ENVJOBS)
+  CARVE(J, float, nr * 8) CARVE(hq, float, 18 * nc + nr) CARVE(Dr, float, nr) CARVE(aref, float, nr) CARVE(jar, float, nr)
+  CARVE(jv, float, nr) CARVE(f, float, nr) CARVE(L, float, 64) CARVE(jq, int, PUSH_ENVJOBS)
   CARVE(sep, float, 4 * (m.npair < PUSH_SEPMAX ? m.npair : PUSH_SEPMAX))
 #undef CARVE
   return off;
@@ -522,10 +523,6 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
 #ifndef PUSH_UNROLL_ROWS
 #define PUSH_UNROLL_ROWS 4
 #endif
-#ifndef PUSH_UNROLL_W
-#define PUSH_UNROLL_W 6
-#endif
-  constexpr int UW = PUSH_UNROLL_W;           // unroll factor of the cone-Hessian row product
   constexpr int UR = PUSH_UNROLL_ROWS;        // unroll factor of the per-dof row loops (gradient, Hessian)
   for (int env0 = blockIdx.x * epb; env0 < a.n; env0 += gridDim.x * epb) {
     const bool valid = env0 + gi < a.n;
@@ -923,70 +920,63 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
 #pragma unroll
         for (int i = 0; i < 8; i++) qfg[i] = (i < NV) ? __shfl_sync(FULL, qf, i, G) : 0.f;
         if (__any_sync(FULL, !stop)) {
-          // ---- W rows (rows across lanes): zone 1 -> D J, zone 2 -> cone Hessian block times the contact's rows
-          if (zone == 2) {
-            float* hc = s.Hc + 36 * g.lane;
-            const float Dm = D[0] / (mu * mu * (1 + mu * mu)), NTv = cN - mu * cT, invT = 1.0f / cT;
-            float U[6], scl[6];
-            const float* pj = s.jar + 6 * g.lane;
-            scl[0] = mu; U[0] = cN;
+          // ---- Hessian J^T (cone Hessians) J as a sum of weighted outer products of Jacobian rows.  Quadratic-zone
+          //      contact: sum_r D_r J_r J_r^T.  Cone-zone contact (U_a = jar_a s_a, u = U / T, s_0 = mu, s_a = fri_a-1,
+          //      k = mu (N - mu T) / T):  Dm (p p^T + k q q^T) - Dm k sum_{a>=1} s_a^2 J_a J_a^T
+          //      with p = mu J_0 - mu sum_{a>=1} u_a s_a J_a and q = sum_{a>=1} u_a s_a J_a -- the 6x6 cone block
+          //      Dm S (v v^T - k (I_t - u u^T)) S of the row formulation, v = e_0 - mu u, never formed.
+          float* const PQ = s.hq; float* const wpq = s.hq + 16 * PUSH_MAXCON; float* const wrow = wpq + 2 * PUSH_MAXCON;
+          {
+            float wr_[6], wp = 0.f, wq = 0.f;
 #pragma unroll
-            for (int j = 1; j < 6; j++) { scl[j] = j < dim ? fri[j - 1] : 0.f; U[j] = j < dim ? pj[j] * fri[j - 1] : 0.f; }
+            for (int r = 0; r < 6; r++) wr_[r] = (zone == 1 && r < dim) ? D[r] : 0.f;
+            if (zone == 2) {
+              const float Dm = D[0] / (mu * mu * (1 + mu * mu)), NTv = cN - mu * cT, invT = 1.0f / cT;
+              const float kap = mu * NTv * invT;
+              const float* pj = s.jar + 6 * g.lane;
+              float pv[8], qv[8];
+              {
+                const push::F8 j = push::ld8(s.J + 8 * (6 * g.lane));
 #pragma unroll
-            for (int aa = 0; aa < 6; aa++)
-#pragma unroll
-              for (int b = 0; b < 6; b++) {
-                float h;
-                if (aa == 0 && b == 0) h = 1.f;
-                else if (aa == 0) h = -mu * U[b] * invT;
-                else if (b == 0) h = -mu * U[aa] * invT;
-                else {
-                  const float uu = U[aa] * U[b] * invT * invT;
-                  h = mu * mu * uu - mu * NTv * ((aa == b ? invT : 0.f) - uu * invT);
-                }
-                hc[6 * aa + b] = (aa < dim && b < dim) ? Dm * scl[aa] * h * scl[b] : 0.f;
+                for (int d = 0; d < 8; d++) { pv[d] = mu * j.v[d]; qv[d] = 0.f; }
               }
-          }
-          // zone bits of this group's contacts: bit c cone, bit 8+c quadratic
-          const unsigned zb2 = (__ballot_sync(FULL, zone == 2) >> g.shift) & 0xffu, zb1 = (__ballot_sync(FULL, zone == 1) >> g.shift) & 0xffu;
-          const unsigned zones = zb2 | (zb1 << 8);
-          __syncwarp();
-          for (int r = g.lane; r < nr_w; r += G) {
-            if (r < nr) {
-              const int c = r / 6, ra = r - 6 * c;
-              float wr[8];
 #pragma unroll
-              for (int d = 0; d < 8; d++) wr[d] = 0.f;
-              if ((zones >> (8 + c)) & 1u) {
-                const push::F8 j = push::ld8(s.J + 8 * r);
-                const float Dv = s.Dr[r];
+              for (int aa = 1; aa < 6; aa++) if (aa < dim) {
+                const float sa = fri[aa - 1];
+                const float cq = pj[aa] * sa * invT * sa, cp = -mu * cq;
+                const push::F8 j = push::ld8(s.J + 8 * (6 * g.lane + aa));
 #pragma unroll
-                for (int d = 0; d < 8; d++) wr[d] = Dv * j.v[d];
-              } else if ((zones >> c) & 1u) {
-                const float* hc = s.Hc + 36 * c + 6 * ra;
-#pragma unroll UW
-                for (int b = 0; b < 6; b++) {
-                  const push::F8 j = push::ld8(s.J + 8 * (6 * c + b));
-                  const float h = hc[b];
-#pragma unroll
-                  for (int d = 0; d < 8; d++) wr[d] += h * j.v[d];
-                }
+                for (int d = 0; d < 8; d++) { pv[d] += cp * j.v[d]; qv[d] += cq * j.v[d]; }
+                wr_[aa] = -Dm * kap * sa * sa;
               }
-              push::st8(s.W + 8 * r, wr);
+              wp = Dm; wq = Dm * kap;
+              push::st8(PQ + 16 * g.lane, pv); push::st8(PQ + 16 * g.lane + 8, qv);
+            }
+            if (g.lane < PUSH_MAXCON) {
+#pragma unroll
+              for (int r = 0; r < 6; r++) wrow[6 * g.lane + r] = wr_[r];
+              wpq[2 * g.lane] = wp; wpq[2 * g.lane + 1] = wq;
             }
           }
           __syncwarp();
-          // ---- Hessian row of this lane's dof: M + J^T W  (+ active limits on the diagonal)
           float Hr[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) Hr[j] = 0.f;
 #pragma unroll UR
           for (int r = sub; r < nr_w; r += SUBS) {
             if (r < nr) {
-              const float ji = s.J[8 * r + li];
-              const push::F8 wv = push::ld8(s.W + 8 * r);
+              const float ji = s.J[8 * r + li] * wrow[r];
+              const push::F8 jv_ = push::ld8(s.J + 8 * r);
 #pragma unroll
-              for (int j = 0; j < 8; j++) Hr[j] += ji * wv.v[j];
+              for (int j = 0; j < 8; j++) Hr[j] += ji * jv_.v[j];
+            }
+          }
+          for (int c = sub; 6 * c < nr_w; c += SUBS) {
+            if (6 * c < nr && wpq[2 * c] != 0.f) {
+              const float pi_ = PQ[16 * c + li] * wpq[2 * c], qi_ = PQ[16 * c + 8 + li] * wpq[2 * c + 1];
+              const push::F8 pv = push::ld8(PQ + 16 * c), qv = push::ld8(PQ + 16 * c + 8);
+#pragma unroll
+              for (int j = 0; j < 8; j++) Hr[j] += pi_ * pv.v[j] + qi_ * qv.v[j];
             }
           }
 #pragma unroll
