@@ -575,8 +575,11 @@ template <typename T> HSR_HD T origin_tri_dist2(V3<T> a, V3<T> b, V3<T> c, V3<T>
 #if defined(__CUDACC__)
 // argmax_i <v_i, l> over a hull stored as float4, lanes of the group striding over the vertices, two vertices per
 // iteration; ties go to the lowest index (as the scalar scan below)
+#ifndef HSR_HULLSCAN_ATTR
+#define HSR_HULLSCAN_ATTR __noinline__
+#endif
 template <typename Grp>
-__device__ __noinline__ int hull_scan4(const float4* __restrict__ v, int n, float lx, float ly, float lz, const Grp& g) {
+__device__ HSR_HULLSCAN_ATTR int hull_scan4(const float4* __restrict__ v, int n, float lx, float ly, float lz, const Grp& g) {
   float best = -FLT_MAX;
   int bi = 0x7fffffff;
   int i = g.lane;
@@ -641,8 +644,17 @@ HSR_HD void mpr_support(const Geom<T>& g1, const Geom<T>& g2, V3<double> d, cons
 // query, which can only end without contact for disjoint shapes); every exit of the query that has such a
 // direction in hand stores it.  Callers without temporal coherence pass nullptr.
 template <typename T, typename Grp>
+HSR_HD bool mpr_penetration_inl(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,
+                                V3<GT>& pdir_, V3<GT>& ppos_, float* sep = nullptr);
+// out-of-line instance (one copy per group type); callers on a hot path with the geoms in registers use _inl directly
+template <typename T, typename Grp>
 HSR_HDN bool mpr_penetration(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,
                              V3<GT>& pdir_, V3<GT>& ppos_, float* sep = nullptr) {
+  return mpr_penetration_inl(g1, g2, tol, max_iter, g, depth_, pdir_, ppos_, sep);
+}
+template <typename T, typename Grp>
+HSR_HD bool mpr_penetration_inl(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,
+                                V3<GT>& pdir_, V3<GT>& ppos_, float* sep) {
   typedef double W;
   auto sup = [&](V3<W> d) { Sup<W> s; mpr_support(g1, g2, d, g, s); return s; };
   auto miss = [&](V3<W> d) {   // disjoint along d: remember the direction

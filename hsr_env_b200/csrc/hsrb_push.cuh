@@ -377,7 +377,9 @@ __device__ __noinline__ int push_collision(const ModelT<float>& m, const push::T
         push_load_geom(m, t, so, t.pair_geom1[pk], A);
         push_load_geom(m, t, so, t.pair_geom2[pk], B);
         GT depth = 0; V3<GT> dir = mk<GT>(0, 0, 1), pos = mk<GT>(0, 0, 0);
-        const bool hit = mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, gw, depth, dir, pos,
+        // inlined instance: the two geoms and the portal stay in registers (the out-of-line one keeps them on the local
+        // stack and reloads them around every support evaluation; +16 % substeps/s)
+        const bool hit = mpr_penetration_inl(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, gw, depth, dir, pos,
                                          pk < PUSH_SEPMAX && !(opts & 1u) ? so.sep + 4 * pk : nullptr);
         if (gw.lane == 0) {
           double* r = blk.res + 8 * j;
