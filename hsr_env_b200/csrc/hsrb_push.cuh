@@ -314,8 +314,11 @@ __device__ __forceinline__ void push_load_geom(const ModelT<float>& m, const pus
 // ---------------------------------------------------------------------------------------------------- collision
 // Candidate pairs -> bounding-sphere + world-AABB cull (one pair per lane) -> narrowphase.  Contacts are appended to
 // the workspace in pair order (plane-box: corner order), exactly as the general kernel's collision() does.
+#ifndef PUSH_COLLISION_ATTR
+#define PUSH_COLLISION_ATTR __noinline__
+#endif
 template <int G>
-__device__ __noinline__ int push_collision(const ModelT<float>& m, const push::Tab& t, push::Ws& s, WS<float>& w,
+__device__ PUSH_COLLISION_ATTR int push_collision(const ModelT<float>& m, const push::Tab& t, push::Ws& s, WS<float>& w,
                                            const DevGrp<G>& g, const push::Blk& blk, unsigned char* smem, unsigned ws_bytes, unsigned opts) {
   int ncon = 0, nrow = 0, narrow = 0, npflop = 0;
   const int gi = threadIdx.x / G;

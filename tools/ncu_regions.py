@@ -8,7 +8,7 @@ import csv,collections,bisect,sys,re
 rows=list(csv.reader(open(sys.argv[1])))
 nwarpsub=float(sys.argv[2])
 src=open('hsr_env_b200/csrc/hsrb_push.cuh').read().splitlines()
-markers=[('impedance5','__device__ __forceinline__ double impedance5'),('collision:cull','__device__ __noinline__ int push_collision'),('collision:jobs','while (__any_sync(0xffffffffu, bits != 0))'),('collision:other','Geom<float> A, B;'),('kernel:setup','hsrb_push_kernel(const __grid_constant__'),('poses','// ---------------------------------------------------------------- poses'),('limits','active joint limits'),('collision:call','// ---------------------------------------------------------------- collision (B.3)'),('smooth','smooth forces (closed form'),('rows','constraint rows: one contact per lane'),('solver:lambdas','Newton solver (B.7)'),('solver:init','bool solving = nefc_true != 0;'),('newton:grad','// ---- gradient component'),('newton:W','// ---- W rows'),('newton:H','// ---- Hessian row'),('newton:chol','// ---- Cholesky H'),('newton:fwd/bwd','// ---- forward solve'),('newton:jv','// ---- jv = J search'),('linesearch','// ---- exact line search'),('newton:update','if (alpha == 0.f) stop = true;'),('goal+euler','goal test on the poses'),('store','results: HBM once per action')]
+markers=[('impedance5','__device__ __forceinline__ double impedance5'),('collision:cull','PUSH_COLLISION_ATTR int push_collision'),('collision:jobs','while (__any_sync(0xffffffffu, bits != 0))'),('collision:other','Geom<float> A, B;'),('kernel:setup','hsrb_push_kernel(const __grid_constant__'),('poses','// ---------------------------------------------------------------- poses'),('limits','active joint limits'),('collision:call','// ---------------------------------------------------------------- collision (B.3)'),('smooth','smooth forces (closed form'),('rows','constraint rows: one contact per lane'),('solver:lambdas','Newton solver (B.7)'),('solver:init','bool solving = nefc_true != 0;'),('newton:grad','// ---- gradient component'),('newton:H','// ---- Hessian J^T (cone Hessians) J'),('newton:chol','// ---- Cholesky H'),('newton:fwd/bwd','// ---- forward solve'),('newton:jv','// ---- jv = J search'),('linesearch','// ---- exact line search'),('newton:update','if (alpha == 0.f) stop = true;'),('goal+euler','goal test on the poses'),('store','results: HBM once per action')]
 push=[]
 for name,pat in markers:
     for i,l in enumerate(src):
@@ -17,7 +17,7 @@ for name,pat in markers:
 push.sort()
 pst=[a for a,_ in push]
 core_src=open('hsr_env_b200/csrc/hsr_core.h').read().splitlines()
-cm=[('groups','struct HostGrp'),('vec3/quat','template <typename T> struct V3'),('workspace','struct WS {'),('kinematics','HSR_HDC void kinematics_lane0'),('geom util','template <typename T> struct Geom'),('make_frame','HSR_HD void make_frame'),('add_contact','HSR_HDC void add_contact'),('mpr:tri','HSR_HD T origin_tri_dist2'),('hull_scan4','__device__ __noinline__ int hull_scan4'),('support_d','HSR_HD V3<double> support_d'),('mpr_support','HSR_HD void mpr_support'),('mpr','HSR_HDN bool mpr_penetration'),('box_box','HSR_HDN void box_box'),('narrow_pair','HSR_HD void narrow_pair'),('impedance','HSR_HD GT impedance'),('solver','HSR_HD int cone_zone'),('flops (+ wait at the block barrier after the solver)','HSR_HD bool model_articulated'),('forward','HSR_HDC void forward')]
+cm=[('groups','struct HostGrp'),('vec3/quat','template <typename T> struct V3'),('workspace','struct WS {'),('kinematics','HSR_HDC void kinematics_lane0'),('geom util','template <typename T> struct Geom'),('make_frame','HSR_HD void make_frame'),('add_contact','HSR_HDC void add_contact'),('mpr:tri','HSR_HD T origin_tri_dist2'),('hull_scan4','__device__ HSR_HULLSCAN_ATTR int hull_scan4'),('support_d','HSR_HD V3<double> support_d'),('mpr_support','HSR_HD void mpr_support'),('mpr','HSR_HD bool mpr_penetration_inl(const Geom<T>& g1, const Geom<T>& g2, GT tol, int max_iter, const Grp& g, GT& depth_,'),('box_box','HSR_HDN void box_box'),('narrow_pair','HSR_HD void narrow_pair'),('impedance','HSR_HD GT impedance'),('solver','HSR_HD int cone_zone'),('flops (+ wait at the block barrier after the solver)','HSR_HD bool model_articulated'),('forward','HSR_HDC void forward')]
 core=[]
 for name,pat in cm:
     for i,l in enumerate(core_src):
