@@ -220,6 +220,10 @@ def run_gpu(args):
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     D.barrier()
     torch.cuda.synchronize(dev)
+    # the workload drifts along the episodes (blocks get pushed away from the base: 36 -> 23 ms per action over 60
+    # actions, tools/step_time_trend.py), so the end-to-end leg below restarts from this snapshot: both legs time the
+    # same actions on the same states
+    snap = [t.clone() for t in env.get_state()] + [done.clone()]
     with ClockSampler(local) as clk:
         for k in range(args.steps):
             flush.fill_(k & 0xff)           # evict L2 between timed iterations (outside the event bracket)
@@ -250,6 +254,8 @@ def run_gpu(args):
     mask_dev = torch.zeros(n, dtype=torch.uint8, device=dev)
     for k in range(min(3, e2e_steps)):  # warm-up of the host path
         env.step_host(act_host[k], out=out)
+    env.set_state(qpos=snap[0], qvel=snap[1], qacc_warmstart=snap[2], mocap_pos=snap[3])
+    out["done"].copy_(snap[4].to(torch.uint8))
     D.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
