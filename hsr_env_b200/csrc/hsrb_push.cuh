@@ -1084,36 +1084,32 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
             else { lq[0] = j0 * mu; lq[1] = v0 * mu; lq[8] = mu; lq[9] = dim > 0 ? D[0] / (mu * mu * (1 + mu * mu)) : 0.f; }
             lq[2] = uu; lq[3] = uv; lq[4] = vv; lq[5] = 0.f; lq[6] = Q1; lq[7] = Q2;
           }
+          // derivative of the cost along the search direction and its slope at alpha; select-only arithmetic (no divergent
+          // branches: the zones of the four environments' contacts differ).  A lane without a contact has all-zero
+          // coefficients and lands in the "top" zone (no force); an inactive limit has sg = D = aref = 0.
           auto ls_eval = [&](float alpha, float& d1, float& d2) {
-            float l1 = 0.f, l2 = 0.f;
-            if (dim > 0) {
-              const float mu_ = lq[8];
-              const float N = lq[0] + alpha * lq[1];
-              const float tsq = lq[2] + alpha * (2 * lq[3] + alpha * lq[4]);
-              const float rT = tsq > 0 ? rsqrtf(tsq) : 0.f;     // 1 / T (used in the cone zone only, where T > 0)
+            const float mu_ = lq[8], Dm = lq[9];
+            const float N = lq[0] + alpha * lq[1];
+            const float tsq = lq[2] + alpha * (2 * lq[3] + alpha * lq[4]);
+            const float rT = tsq > 0 ? rsqrtf(tsq) : 0.f;     // 1 / T (used in the cone zone only, where T > 0)
             const float Tn = tsq * rT;
-              bool top = (N >= mu_ * Tn) || (Tn <= 0 && N >= 0);
-              bool bottom = (mu_ * N + Tn <= 0) || (Tn <= 0 && N < 0);
-              if (lq[9] < 0) { top = !(N < 0); bottom = N < 0; }
-              if (!top) {
-                if (bottom) { l1 = lq[6] + 2 * alpha * lq[7]; l2 = 2 * lq[7]; }
-                else {
-                  const float Dm = lq[9];
-                  const float NTv = N - mu_ * Tn;
-                  const float N1 = lq[1];
-                    const float T1 = (lq[3] + alpha * lq[4]) * rT;
-                  const float T2 = (lq[4] - T1 * T1) * rT;
-                  l1 = Dm * NTv * (N1 - mu_ * T1);
-                  l2 = Dm * ((N1 - mu_ * T1) * (N1 - mu_ * T1) - NTv * mu_ * T2);
-                }
-              }
-            }
+            const bool quad = Dm < 0;                          // condim-1 contact: half-line instead of a cone
+            const bool top = quad ? !(N < 0) : ((N >= mu_ * Tn) || (Tn <= 0 && N >= 0));
+            const bool bottom = quad ? (N < 0) : ((mu_ * N + Tn <= 0) || (Tn <= 0 && N < 0));
+            const float NTv = N - mu_ * Tn;
+            const float T1 = (lq[3] + alpha * lq[4]) * rT;
+            const float T2 = (lq[4] - T1 * T1) * rT;
+            const float tt = lq[1] - mu_ * T1;
+            const float lm1 = Dm * NTv * tt, lm2 = Dm * (tt * tt - NTv * mu_ * T2);
+            const float lb1 = lq[6] + 2 * alpha * lq[7], lb2 = 2 * lq[7];
+            float l1 = top ? 0.f : (bottom ? lb1 : lm1), l2 = top ? 0.f : (bottom ? lb2 : lm2);
             l1 = gsum(l1); l2 = gsum(l2);
 #pragma unroll
-            for (int j = 0; j < 2; j++) if (lim_sg[j] != 0.f) {
+            for (int j = 0; j < 2; j++) {
               const float xv = lim_sg[j] * srch[j];
               const float xx = lim_sg[j] * x[j] - lim_aref[j] + alpha * xv;
-              if (xx < 0) { l1 += lim_D[j] * xx * xv; l2 += lim_D[j] * xv * xv; }
+              const float dd = xx < 0 ? lim_D[j] : 0.f;
+              l1 += dd * xx * xv; l2 += dd * xv * xv;
             }
             d1 = l1 + q1 + 2 * alpha * q2;
             d2 = l2 + 2 * q2;
