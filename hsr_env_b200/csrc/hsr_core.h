@@ -431,6 +431,47 @@ template <typename T> HSR_HDC void chol_solve(const T* L, int n, T* x) {
   }
 }
 
+// The same factorisation / solves with the lanes of a group sharing the rows (A in the environment's shared-memory
+// workspace).  Column k: every row i >= k forms its dot product with row k in the serial routine's order (so L is
+// bit-identical to chol_factor's), then the rows below the diagonal are scaled.  The solves are column-oriented: once
+// x[i] is final the lanes subtract its column from the remaining entries.  With one lane (host port) this is the
+// serial algorithm.
+template <typename T, typename Grp> HSR_HD bool chol_factor_g(T* A, int n, const Grp& g) {
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    for (int i = k + g.lane; i < n; i += Grp::G) {
+      T s = A[i * n + k];
+      for (int j = 0; j < k; j++) s -= A[i * n + j] * A[k * n + j];
+      A[i * n + k] = s;
+    }
+    g.sync();
+    T d = A[k * n + k];
+    if (!(d > Lim<T>::minval())) { d = Lim<T>::minval(); ok = false; }
+    d = sqrt(d);
+    const T inv = T(1) / d;
+    g.sync();   // every lane has read the pivot
+    for (int i = k + g.lane; i < n; i += Grp::G) A[i * n + k] = (i == k) ? d : A[i * n + k] * inv;
+    g.sync();
+  }
+  return ok;
+}
+template <typename T, typename Grp> HSR_HD void chol_solve_g(const T* L, int n, T* x, const Grp& g) {
+  for (int i = 0; i < n; i++) {        // L y = b
+    const T xi = x[i] / L[i * n + i];
+    g.sync();
+    if (g.lane == 0) x[i] = xi;
+    for (int r = i + 1 + g.lane; r < n; r += Grp::G) x[r] -= L[r * n + i] * xi;
+    g.sync();
+  }
+  for (int i = n - 1; i >= 0; i--) {   // L^T x = y
+    const T xi = x[i] / L[i * n + i];
+    g.sync();
+    if (g.lane == 0) x[i] = xi;
+    for (int r = g.lane; r < i; r += Grp::G) x[r] -= L[i * n + r] * xi;
+    g.sync();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ B.6 smooth dynamics
 template <typename T> HSR_HD void cross_motion(const T* v, const T* s, T* r) {
   V3<T> va = ld3(v), vl = ld3(v + 3), sa = ld3(s), sl = ld3(s + 3);
@@ -441,7 +482,7 @@ template <typename T> HSR_HD void cross_force(const T* v, const T* f, T* r) {
   st3(r, cross(va, fa) + cross(vl, fl)); st3(r + 3, cross(va, fl));
 }
 
-// lane 0: RNE bias, passive, actuation -> qfrc_smooth; factor M -> L; qacc_smooth
+// lane 0: RNE bias, passive, actuation -> qfrc_smooth
 template <typename T>
 HSR_HDC void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
   int nv = m.nv;
@@ -490,10 +531,16 @@ HSR_HDC void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
     if (m.act_forcelimited[a]) f = fmin(fmax(f, m.act_forcerange[2 * a]), m.act_forcerange[2 * a + 1]);
     w.qfrc_smooth[m.act_dof[a]] += m.act_gear[a] * f;
   }
-  for (int k = 0; k < nv * nv; k++) w.L[k] = w.M[k];
-  if (!chol_factor(w.L, nv)) w.wi[WI_FLAGS] |= FLAG_CHOL;
-  for (int i = 0; i < nv; i++) w.qacc_smooth[i] = w.qfrc_smooth[i];
-  chol_solve(w.L, nv, w.qacc_smooth);
+}
+// factor M -> L and qacc_smooth = M^-1 qfrc_smooth, rows across the lanes of the group
+template <typename T, typename Grp>
+HSR_HD void smooth_solve(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  const int nv = m.nv;
+  for (int k = g.lane; k < nv * nv; k += Grp::G) w.L[k] = w.M[k];
+  for (int i = g.lane; i < nv; i += Grp::G) w.qacc_smooth[i] = w.qfrc_smooth[i];
+  g.sync();
+  if (!chol_factor_g(w.L, nv, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
+  chol_solve_g(w.L, nv, w.qacc_smooth, g);
 }
 
 // ------------------------------------------------------------------------------------------------ B.3 collision
@@ -889,7 +936,11 @@ HSR_HD void narrow_pair(const ModelT<T>& m, WS<T>& w, const Grp& g, int pk, int&
     box_box(m, w, g, ncon, nrow, pk, A, B);
   } else {
     GT depth; V3<GT> dir, pos;
+#if !defined(HSR_COMPACT)   // shared-memory kernel: the inlined query keeps the geoms in registers (C3 +4 %)
+    if (mpr_penetration_inl(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+#else
     if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+#endif
       add_contact(m, w, g, ncon, nrow, pk, -depth, pos, dir);
   }
 }
@@ -1267,13 +1318,10 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
       for (int r = 0; r < nefc; r++) s += w.J[r * nv + a] * w.W[r * nv + b];
       w.H[a * nv + b] = s;
     }
+    for (int i = g.lane; i < nv; i += Grp::G) w.search[i] = -w.grad[i];
     g.sync();
-    if (g.lane == 0) {
-      if (!chol_factor(w.H, nv)) w.wi[WI_FLAGS] |= FLAG_CHOL;
-      for (int i = 0; i < nv; i++) w.search[i] = -w.grad[i];
-      chol_solve(w.H, nv, w.search);
-    }
-    g.sync();
+    if (!chol_factor_g(w.H, nv, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
+    chol_solve_g(w.H, nv, w.search, g);
     T sn = 0, dec = 0;
     for (int i = g.lane; i < nv; i += Grp::G) { sn += w.search[i] * w.search[i]; dec -= w.grad[i] * w.search[i]; }
     sn = sqrt(g.sum(sn));
@@ -1322,20 +1370,29 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
 }
 
 // ------------------------------------------------------------------------------------------------ B.8 Euler
+// qacc_int = (M + dt*diag(damping))^-1 (qfrc_smooth + qfrc_constraint) -> w.grad, rows across the lanes of the group
+template <typename T, typename Grp>
+HSR_HD void euler_solve(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  const int nv = m.nv;
+  const T dt = m.timestep;
+  T* x = w.grad;  // scratch
+  if (m.any_damping) {
+    for (int k = g.lane; k < nv * nv; k += Grp::G) { const int i = k / nv; w.H[k] = w.M[k] + ((k - i * nv == i) ? dt * m.dof_damping[i] : T(0)); }
+    for (int i = g.lane; i < nv; i += Grp::G) x[i] = w.qfrc_smooth[i] + w.tmpv[i];
+    g.sync();
+    if (!chol_factor_g(w.H, nv, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
+    chol_solve_g(w.H, nv, x, g);
+  } else {
+    for (int i = g.lane; i < nv; i += Grp::G) x[i] = w.qacc[i];
+    g.sync();
+  }
+}
+// lane 0: semi-implicit Euler with the accelerations of euler_solve
 template <typename T>
 HSR_HDC void euler_lane0(const ModelT<T>& m, WS<T>& w) {
   int nv = m.nv;
   T dt = m.timestep;
-  // qacc_int = (M + dt*diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
-  T* x = w.grad;  // scratch
-  if (m.any_damping) {
-    for (int k = 0; k < nv * nv; k++) w.H[k] = w.M[k];
-    for (int i = 0; i < nv; i++) { w.H[i * nv + i] += dt * m.dof_damping[i]; x[i] = w.qfrc_smooth[i] + w.tmpv[i]; }
-    if (!chol_factor(w.H, nv)) w.wi[WI_FLAGS] |= FLAG_CHOL;
-    chol_solve(w.H, nv, x);
-  } else {
-    for (int i = 0; i < nv; i++) x[i] = w.qacc[i];
-  }
+  T* x = w.grad;
   bool bad = false;
   for (int i = 0; i < nv; i++) {
     w.warm[i] = w.qacc[i];
@@ -1407,6 +1464,8 @@ HSR_HDC void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   g.sync();
   HSR_PHASE(w, g, PH_CRB);
   if (g.lane == 0) smooth_lane0(m, w);
+  g.sync();
+  smooth_solve(m, w, g);
   HSR_PHASE(w, g, PH_SMOOTH);
   // active joint limits (uniform count)
   int nlimit = 0;
@@ -1439,6 +1498,7 @@ HSR_HDC void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
 template <typename T, typename Grp>
 HSR_HD void substep(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   forward(m, w, g);
+  euler_solve(m, w, g);
   if (g.lane == 0) euler_lane0(m, w);
   g.sync();
   HSR_PHASE(w, g, PH_EULER);

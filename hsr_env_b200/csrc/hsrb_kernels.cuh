@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
       taken = env_action(a.m, a.cfg, w, g, a.nsub, success);
     } else if (a.mode == MODE_DEBUG) {
       forward(a.m, w, g);
+      euler_solve(a.m, w, g);
       if (g.lane == 0) euler_lane0(a.m, w);
       g.sync();
       if (g.lane == 0) debug_dump(a.m, w, a.dump + (size_t)env * a.dump_stride);

@@ -62,6 +62,7 @@ void run_range(Handle* h, int lo, int hi, int nsub, const double* qpos, const do
       T q0[64], v0[32];
       for (int i = 0; i < m.nq; i++) q0[i] = w.qpos[i];
       for (int i = 0; i < m.nv; i++) v0[i] = w.qvel[i];
+      euler_solve(m, w, g);
       euler_lane0(m, w);
       debug_dump(m, w, dbg + (size_t)e * dsz);
       ok = goal_reached(m, cfg, w);

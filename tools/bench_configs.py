@@ -54,6 +54,9 @@ def run(name, blob, n, pan, steps=3, warmup=2, nsub=300, lanes=0):
             "mean_contacts_per_substep": (st1["contacts"] - st0["contacts"]) / max(1.0, sub),
             "mean_newton_iters_per_substep": (st1["newton_iters"] - st0["newton_iters"]) / max(1.0, sub),
             "bad_envs": st1["bad_envs"] - st0["bad_envs"]}
+    ph = {k: st1["phase_cycles"][k] - st0["phase_cycles"][k] for k in st1["phase_cycles"]}
+    if sum(ph.values()) > 0:
+        line["phase_share"] = {k: round(v / sum(ph.values()), 3) for k, v in ph.items()}
     env.close()
     print(json.dumps(line), flush=True)
 
