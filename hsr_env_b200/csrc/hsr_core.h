@@ -214,6 +214,7 @@ struct WS {
   T *lsq;
   int *con_pair, *con_adr, *con_zone;
   int* wi;
+  float* sep;   // [npair][4] cached separating direction + valid flag of each candidate pair (mpr_penetration's `sep`)
 };
 
 // Carve the workspace out of `base` (nullptr: just return the size in bytes).
@@ -236,6 +237,7 @@ HSR_HD size_t ws_carve(const ModelT<T>& m, WS<T>* w, unsigned char* base) {
   CARVE(J, T, ne * nv) CARVE(W, T, ne * nv) CARVE(D, T, ne) CARVE(aref, T, ne) CARVE(jar, T, ne) CARVE(jv, T, ne)
   CARVE(force, T, ne) CARVE(lsq, T, nc * HSR_LSQ)
   CARVE(con_pair, int, nc) CARVE(con_adr, int, nc) CARVE(con_zone, int, nc) CARVE(wi, int, WI_COUNT)
+  CARVE(sep, float, 4 * m.npair)
 #undef CARVE
   off += (16 - off % 16) % 16;
   return off;
@@ -937,7 +939,11 @@ HSR_HD void narrow_pair(const ModelT<T>& m, WS<T>& w, const Grp& g, int pk, int&
   } else {
     GT depth; V3<GT> dir, pos;
 #if !defined(HSR_COMPACT)   // shared-memory kernel: the inlined query keeps the geoms in registers (C3 +4 %)
-    if (mpr_penetration_inl(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
+    float* sp = nullptr;
+#if defined(__CUDA_ARCH__)
+    sp = w.sep + 4 * pk;       // device only: the host port stays the plain query
+#endif
+    if (mpr_penetration_inl(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos, sp))
 #else
     if (mpr_penetration(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos))
 #endif

@@ -48,6 +48,7 @@ __device__ __forceinline__ void load_state(const KArgs& a, WS<float>& w, const D
   for (int i = g.lane; i < n0; i += G) w.qpos[i] = st[i];  // qpos|qvel|warm are contiguous in the workspace
   for (int i = g.lane; i < 3; i += G) w.mocap[i] = st[n0 + i];
   for (int i = g.lane; i < WI_COUNT; i += G) w.wi[i] = 0;
+  for (int i = g.lane; i < 4 * a.m.npair; i += G) w.sep[i] = 0.f;   // no cached separating directions
 }
 template <int G>
 __device__ __forceinline__ void store_state(const KArgs& a, WS<float>& w, const DevGrp<G>& g, int env) {

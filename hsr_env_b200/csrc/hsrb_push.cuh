@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
   WS<float> w;                                // view for the shared narrowphase routines (hsr_core.h)
   w.xpos = s.xpos; w.xmat = s.xmat; w.gpos = s.gpos; w.gaabb = s.gaabb;
   w.con_dist = s.con_dist; w.con_pos = s.con_pos; w.con_frame = s.con_frame;
-  w.con_pair = s.con_pair; w.con_adr = s.con_adr; w.wi = s.wi;
+  w.con_pair = s.con_pair; w.con_adr = s.con_adr; w.wi = s.wi; w.sep = nullptr;
   const ModelT<float>& m = a.m;
   const int nq = m.nq;
   const float dt = m.timestep;
