@@ -24,12 +24,16 @@ from hsr_env_b200.model import Model  # noqa: E402
 from oracle import mjstep, port  # noqa: E402
 from scenarios import rollout_states  # noqa: E402
 
-CASES = {"c1_readme": (12, False), "c1b_readme_block": (12, False), "c2_push": (24, False), "c3_arm": (8, True), "c5_clutter": (8, False)}
+CASES = {"c1_readme": (12, False), "c1b_readme_block": (12, False), "c2_push": (24, False), "c3_arm": (8, True), "c5_clutter": (8, False),
+         "f2_cupboard": (8, True)}
 
 
 def main():
     out = Path(__file__).resolve().parent
+    only = sys.argv[1:]
     for name, (n, pan) in CASES.items():
+        if only and name not in only:
+            continue
         model = Model.load(ROOT / "hsr_env_b200" / "blobs" / f"{name}.hsrb")
         cp = port.CpuPort(model)
         qpos, qvel, warm, ctrl = rollout_states(cp, model, n, seed=1234 + len(name), pan=pan, float32=True)

@@ -7,7 +7,7 @@ import pytest
 from conftest import GOLDEN
 from scenarios import rel_err
 
-NAMES = ["c1_readme", "c1b_readme_block", "c2_push", "c3_arm", "c5_clutter"]
+NAMES = ["c1_readme", "c1b_readme_block", "c2_push", "c3_arm", "c5_clutter", "f2_cupboard"]
 
 
 def load(name):
@@ -64,7 +64,8 @@ def test_cuda_matches_golden(name, models):
     assert np.mean(ev > 1e-4) <= 0.05, np.sort(ev)[-3:]
     if goals and m.nblock == 1:
         # bit-exact flags wherever the block is not within fp32 rounding of the geofence
-        d = np.linalg.norm(g["qpos"][:, 2:5] - g["mocap"], axis=1)
+        a = 2 if name != "f2_cupboard" else 0   # qpos address of the block's free joint
+        d = np.linalg.norm(g["qpos"][:, a:a + 3] - g["mocap"], axis=1)
         clear = np.abs(d - np.float32(.05)) > 1e-6
         assert np.array_equal(done.cpu().numpy().astype(np.uint8)[clear], g["success"][clear])
     env.close()

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
 CASES = [("c1_readme", 64, False, "general"), ("c2_push", 256, False, "general"), ("c1b_readme_block", 64, False, "general"),
-         ("c5_clutter", 64, False, "general"), ("c3_arm", 64, True, "general"),
+         ("c5_clutter", 64, False, "general"), ("c3_arm", 64, True, "general"), ("f2_cupboard", 64, True, "general"),
          ("c1_readme", 64, False, "fast"), ("c2_push", 256, False, "fast"), ("c1b_readme_block", 64, False, "fast")]
 
 
@@ -205,3 +205,36 @@ def test_fast_kernel_matches_general_kernel_along_rollouts():
     print(f"fast vs general kernel: {over} of {total} environment-substeps differ by more than {TOL}")
     assert over <= total * 0.002
     fast.close(); gen.close()
+
+
+def test_reference_smoke_loop_form_on_the_cupboard_scene():
+    """The reference's own example (hsr/__init__.py:9-28): cupboard scene, GoalSpec(a='block', b=array, distance),
+    starts={'blockjoint': 7-d Box}; reset / step(action_space.sample()) / reset-on-done, 20 steps per episode."""
+    from hsr_env_b200.env import BatchedHSREnv
+    from hsr_env_b200.spaces import Box
+    from hsr_env_b200.util import GoalSpec
+
+    n = 32
+    #                                            x    y    z    q1 q2  q3 q4      (hsr/__init__.py:15-17)
+    starts = {"blockjoint": Box(low=np.array([-.1, -.2, .418, 0, 0, -1, 0]), high=np.array([.1, .2, .418, 1, 0, 1, 0]))}
+    env = BatchedHSREnv("f2_cupboard.hsrb", [GoalSpec(a="block", b=np.array([0, 0, .498]), distance=.05)], starts=starts,
+                        steps_per_action=20, n_envs=n, device="cuda:0")
+    assert env.launch_info()["kernel"] == "general"      # block body first, robot second: not the sliding-base family
+    obs = env.reset()
+    q = obs[:, :env.nq].cpu().numpy()
+    assert np.all(q[:, 0] >= -.1 - 1e-6) and np.all(q[:, 0] <= .1 + 1e-6) and np.allclose(q[:, 2], .418)
+    assert np.all(q[:, 4] == 0) and np.all(q[:, 6] == 0)                # quaternion x, z components of the start space
+    assert np.allclose(np.linalg.norm(q[:, 3:7], axis=1), 1, atol=1e-6)   # sim.forward() normalised it
+    total_done = 0
+    for t in range(20):
+        act = torch.tensor(np.stack([env.action_space.sample() for _ in range(n)]), dtype=torch.float32)
+        obs, reward, done, info = env.step(act)
+        assert torch.isfinite(obs).all() and int(info["bad_state"].sum()) == 0
+        assert torch.equal(reward > 0, done)
+        total_done += int(done.sum())
+        if done.any():
+            env.reset(mask=done)
+    # the block rests on the pan ~7.6 cm below the goal point: with a 5 cm geofence the episode never succeeds
+    assert total_done == 0
+    assert np.all(obs[:, 2].cpu().numpy() > .40)                        # still on the pan
+    env.close()

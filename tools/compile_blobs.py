@@ -23,6 +23,8 @@ CONFIGS = {
     "c2_push": (SLIDE, 1, [(-0.15, 0.0, 0.017)]),                  # block on the floor in front of the base
     "c3_arm": (ALL_DOFS, 1, [(0.0, 0.0, 0.422)]),                  # block on the pan, 7 robot dofs
     "c5_clutter": (SLIDE, 4, [(-0.20, -0.12, 0.017), (-0.08, -0.10, 0.017), (-0.20, 0.05, 0.017), (-0.07, 0.06, 0.017)]),
+    # the scene of the reference's own smoke loop (hsr/__init__.py:9-28): cupboard + its `block` body
+    "f2_cupboard": (SLIDE, 0, [], "cupboard-world.xml"),
 }
 
 
@@ -34,8 +36,10 @@ def main():
     args = ap.parse_args()
     args.out.mkdir(exist_ok=True, parents=True)
     opts = mjcf.CompileOptions(mesh_inertia=args.mesh_inertia)
-    for name, (dofs, nb, pos) in CONFIGS.items():
-        m = mjcf.compile_model(args.assets / "models" / "world.xml", dofs, n_blocks=nb, block_pos=pos, opts=opts)
+    for name, cfg in CONFIGS.items():
+        dofs, nb, pos = cfg[:3]
+        xml = cfg[3] if len(cfg) > 3 else "world.xml"
+        m = mjcf.compile_model(args.assets / "models" / xml, dofs, n_blocks=nb, block_pos=pos, opts=opts)
         m.save_with_names(args.out / f"{name}.hsrb")
         print(f"{name}: nq={m.nq} nv={m.nv} nu={m.nu} nbody={m.nbody} ngeom={m.ngeom} npair={m.npair} "
               f"nvert={m.nvert} bytes={len(m.to_blob())}")
