@@ -215,6 +215,8 @@ class BatchedHSREnv:
                 sel = mask.bool()
                 qpos[sel, a:a + w] = draw[sel]
         self.set_state(qpos, qvel)
+        self.body_xpos()   # sim.forward() (hsr/env.py:176): normalises the free-joint quaternions in qpos
+        qpos, qvel, _, _ = self.get_state()
         return torch.cat([qpos, qvel], dim=1)
 
     def step(self, action: torch.Tensor, steps: Optional[int] = None):

@@ -20,14 +20,17 @@ def initial_states(model, n, seed, pan=False):
     random yaw, not overlapping each other or the robot."""
     rng = np.random.default_rng(seed)
     q = np.tile(model.qpos0, (n, 1))
-    names = {int(model.jnt_qposadr[j]): j for j in range(model.njnt)}
+    first_slide = min(j for j in range(model.njnt) if model.jnt_type[j] != 0)
+    cupboard = "blockjoint" in list(model.names.get("joint", []))
     for j in range(model.njnt):
         if model.jnt_type[j] == 0:
             continue
         a = model.jnt_qposadr[j]
         lo, hi = (model.jnt_range[j] if model.jnt_limited[j] else (-0.5, 0.0))
-        if j == 0:
-            lo, hi = -0.05, 0.12   # slide_x: keeps the base clear of the pan edge and of the joint limits
+        if j == first_slide:
+            # slide_x: keeps the base clear of the pan edge and of the joint limits; in the cupboard scene (its own
+            # `blockjoint`) also keeps the arm out of the cupboard doors (16 cm deep at the upper joint limit)
+            lo, hi = (-0.05, 0.02) if cupboard else (-0.05, 0.12)
         q[:, a] = rng.uniform(lo, hi, n)
     for e in range(n):
         placed = []
