@@ -687,7 +687,8 @@ HSR_HD void mpr_support(const Geom<T>& g1, const Geom<T>& g2, V3<double> d, cons
 
 // Minkowski Portal Refinement penetration query (libccd ccdMPRPenetration as used by mjc_Convex).
 //
-// `sep` (optional, 4 floats: direction + valid flag) caches a separating direction of the pair between calls: a
+// `sep` (optional, 4 floats: direction + flag; flag 1 = direction valid, 2 = the pair was in contact, 0 = nothing
+// known) caches a separating direction of the pair between calls: a
 // direction d with max <a - b, d> < 0 proves the shapes disjoint, so a later call first spends one support
 // evaluation on the cached direction and returns "no contact" if it still separates (same decision as the full
 // query, which can only end without contact for disjoint shapes); every exit of the query that has such a
@@ -710,7 +711,7 @@ HSR_HD bool mpr_penetration_inl(const Geom<T>& g1, const Geom<T>& g2, GT tol, in
     if (sep && g.lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = 1.f; }
     return false;
   };
-  if (sep && sep[3] != 0.f) {
+  if (sep && sep[3] == 1.f) {
     V3<W> dc = normalized(mk<W>((W)sep[0], (W)sep[1], (W)sep[2]));
     Sup<W> sc = sup(dc);
     W dtc = dot(sc.v, dc);
@@ -734,6 +735,7 @@ HSR_HD bool mpr_penetration_inl(const Geom<T>& g1, const Geom<T>& g2, GT tol, in
   };
   auto finish = [&](W depth, V3<W> dir, V3<W> pos) {
     depth_ = depth; pdir_ = dir; ppos_ = pos;
+    if (sep && g.lane == 0) sep[3] = 2.f;   // in contact: the next query of this pair is a long one (job ordering)
     return true;
   };
   const W eps = Lim<W>::eps();

@@ -352,8 +352,13 @@ __device__ PUSH_COLLISION_ATTR int push_collision(const ModelT<float>& m, const 
         bb &= bb - 1;
         if (t.pair_func[base + l] != NP_CONVEX_CONVEX) continue;
         if (nq < PUSH_ENVJOBS) {
-          int j = atomicAdd(blk.ctr, 1);
-          if (j < PUSH_MAXJOBS) blk.jobs[j] = (gi << 16) | (base + l); else j = -1;
+          // longest jobs first: a pair without a cached separating direction (in contact last time, or new) is a full
+          // refinement (~11 support evaluations) and goes to the front half of the queue, a pair with one is usually a
+          // single support evaluation and goes to the back half, which the warps serve afterwards
+          const int pk_ = base + l;
+          const bool quick = pk_ < PUSH_SEPMAX && !(opts & 1u) && s.sep[4 * pk_ + 3] == 1.f;
+          int j = atomicAdd(blk.ctr + (quick ? 2 : 0), 1);
+          if (j < PUSH_MAXJOBS / 2) { j += quick ? PUSH_MAXJOBS / 2 : 0; blk.jobs[j] = (gi << 16) | pk_; } else j = -1;
           s.jq[nq] = j;
         }
         nq++;
@@ -364,13 +369,20 @@ __device__ PUSH_COLLISION_ATTR int push_collision(const ModelT<float>& m, const 
     //      dynamically, results go to the queue's result records
     {
       DevGrp<32> gw;
-      int total = blk.ctr[0];
-      if (total > PUSH_MAXJOBS) total = PUSH_MAXJOBS;
+      int total = blk.ctr[0], slot0 = 0;
+      int* next = blk.ctr + 1;
+      if (total > PUSH_MAXJOBS / 2) total = PUSH_MAXJOBS / 2;
       while (true) {
         int j = 0;
-        if (gw.lane == 0) j = atomicAdd(blk.ctr + 1, 1);
+        if (gw.lane == 0) j = atomicAdd(next, 1);
         j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= total) break;
+        if (j >= total) {
+          if (slot0) break;
+          slot0 = PUSH_MAXJOBS / 2; next = blk.ctr + 3; total = blk.ctr[2];   // then the quick half
+          if (total > PUSH_MAXJOBS / 2) total = PUSH_MAXJOBS / 2;
+          continue;
+        }
+        j += slot0;
         const int code = blk.jobs[j];
         const int pk = code & 0xffff;
         push::Ws so;
@@ -458,7 +470,7 @@ __device__ PUSH_COLLISION_ATTR int push_collision(const ModelT<float>& m, const 
     }
     // the queue is empty again for the next chunk / substep (every thread is past the two barriers above and nothing is
     // queued before the next one)
-    if (threadIdx.x == 0) { blk.ctr[0] = 0; blk.ctr[1] = 0; }
+    if (threadIdx.x == 0) { blk.ctr[0] = 0; blk.ctr[1] = 0; blk.ctr[2] = 0; blk.ctr[3] = 0; }
     if (base + 32 < m.npair) __syncthreads();
   }
   if (g.lane == 0) { s.wi[WI_NARROW] += narrow; s.wi[WI_NPFLOP] = npflop; }
@@ -485,7 +497,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
     push::carve_tail(a.m, tail, &s.verts4, &blk);
     float* v4 = reinterpret_cast<float*>(tail);
     for (int i = threadIdx.x; i < a.m.nvert * 4; i += blockDim.x) v4[i] = fi.verts4[i];
-    if (threadIdx.x == 0) { blk.ctr[0] = 0; blk.ctr[1] = 0; }
+    if (threadIdx.x == 0) { blk.ctr[0] = 0; blk.ctr[1] = 0; blk.ctr[2] = 0; blk.ctr[3] = 0; }
   }
   push::Tab t;
   {
