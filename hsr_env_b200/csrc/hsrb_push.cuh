@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(G == 16 ? 448 : 256) hsrb_push_kernel(const __
   // on a copy; its results were written when it finished and nothing is stored afterwards.
   constexpr unsigned FULL = 0xffffffffu;
 #ifndef PUSH_UNROLL_ROWS
-#define PUSH_UNROLL_ROWS 4
+#define PUSH_UNROLL_ROWS 6
 #endif
   constexpr int UR = PUSH_UNROLL_ROWS;        // unroll factor of the per-dof row loops (gradient, Hessian)
   for (int env0 = blockIdx.x * epb; env0 < a.n; env0 += gridDim.x * epb) {
