@@ -90,9 +90,10 @@ class BatchedHSREnv:
         if any([render, record, render_freq, record_freq, record_path]):
             raise NotImplementedError("render/record need an OpenGL viewer and are outside the batched backend "
                                       "(SURVEY.md §8f row f4)")
-        if obs_type not in (None, "qpos-qvel"):
-            raise NotImplementedError(f"obs_type={obs_type!r}: only the default qpos|qvel observation "
-                                      "(hsr/env.py:111-113) is implemented")
+        if obs_type not in (None, "qpos-qvel", "openai"):
+            raise NotImplementedError(f"obs_type={obs_type!r}: the default qpos|qvel observation (hsr/env.py:111-113) and "
+                                      "'openai' (hsr/env.py:72-110) are implemented")
+        self._obs_type = obs_type
         self.model = load_model(xml_file)
         self.starts = dict(starts or {})
         self.goals_specs = list(goals) if goals else []
@@ -116,7 +117,8 @@ class BatchedHSREnv:
         self.kernel_path = _lib.check(self._lib.hsrb_set_path(self._h, {"auto": 0, "general": 1, "fast": 2}[kernel]))
         m = self.model
         self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
-        self.obs_dim = self.nq + self.nv
+        self.state_dim = self.nq + self.nv   # what the kernel writes: qpos | qvel
+        self.obs_dim = 25 if obs_type == "openai" else self.state_dim
         # spaces (mujoco_env.py:44-56)
         self.action_space = Box(m.act_ctrlrange[:, 0], m.act_ctrlrange[:, 1], dtype=np.float32)
         high = np.inf * np.ones(self.obs_dim)
@@ -190,14 +192,14 @@ class BatchedHSREnv:
             self._push_goals(True)
         else:
             self._push_goals(False)
-        obs = self._empty(self.n_envs, self.obs_dim)
+        obs = self._empty(self.n_envs, self.state_dim)
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_reset(self._h, _lib.ptr(mask), _lib.ptr(obs), self._stream()))
             if self.starts:
                 obs = self._apply_starts(mask)
-        return obs
+        return self._observation(obs)
 
     def _apply_starts(self, mask):
         """new_state (hsr/env.py:149-156): qpos slices of named joints drawn from their start spaces."""
@@ -223,7 +225,7 @@ class BatchedHSREnv:
         """HSREnv.step (hsr/env.py:115-135) for every environment: one kernel launch."""
         steps = steps or self.steps_per_action
         action = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(self.n_envs, self.nu).contiguous()
-        obs = self._empty(self.n_envs, self.obs_dim)
+        obs = self._empty(self.n_envs, self.state_dim)
         reward = self._empty(self.n_envs)
         done = self._empty(self.n_envs, dtype=torch.uint8)
         taken = self._empty(self.n_envs, dtype=torch.int32)
@@ -234,19 +236,34 @@ class BatchedHSREnv:
         self._time_steps += 1
         done_b = done.bool()
         info = {"log count": {"success": done_b}, "substeps_taken": taken, "bad_state": bad}
-        return obs, reward, done_b, info
+        return self._observation(obs), reward, done_b, info
 
     def step_host(self, action: np.ndarray, steps: Optional[int] = None, out=None):
         """Same call with HOST buffers (numpy / pinned torch CPU tensors), copies inside: the end-to-end path."""
+        if self._obs_type == "openai":
+            raise NotImplementedError("step_host returns the kernel's qpos|qvel observation; use step() for obs_type='openai'")
         steps = steps or self.steps_per_action
         if out is None:
-            out = dict(obs=np.empty((self.n_envs, self.obs_dim), np.float32), reward=np.empty(self.n_envs, np.float32),
+            out = dict(obs=np.empty((self.n_envs, self.state_dim), np.float32), reward=np.empty(self.n_envs, np.float32),
                        done=np.empty(self.n_envs, np.uint8), taken=np.empty(self.n_envs, np.int32))
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_step_host(self._h, _lib.ptr(action), int(steps), _lib.ptr(out["obs"]),
                                                 _lib.ptr(out["reward"]), _lib.ptr(out["done"]), _lib.ptr(out["taken"])))
         self._time_steps += 1
         return out
+
+    def _observation(self, state: torch.Tensor) -> torch.Tensor:
+        """HSREnv._get_observation (hsr/env.py:71-113): the kernel's qpos|qvel, or the 25-d 'openai' observation built
+        from it on the device (hsr_env_b200/kin.py states the intent of the reference's dead branch)."""
+        if self._obs_type != "openai":
+            return state
+        from . import kin
+
+        if not len(self.model.block_body):
+            raise NotImplementedError("the 'openai' observation needs a block (hsr/env.py:58 `_block_name`)")
+        obs = kin.openai_observation(self.model, state[:, :self.nq], state[:, self.nq:], float(self.model.timestep),
+                                     int(self.model.block_body[0]))
+        return obs.to(torch.float32)
 
     def compute_reward(self) -> torch.Tensor:
         """float(all in_range) of the current state (north star name; hsr/env.py:126,133)."""

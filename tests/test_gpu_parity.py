@@ -244,3 +244,69 @@ def test_reference_smoke_loop_form_on_the_cupboard_scene():
     assert total_done <= n
     assert np.all(obs[:, 2].cpu().numpy() > .40)                        # still on the pan
     env.close()
+
+
+def test_full_size_properties_of_the_bench_workload():
+    """BASELINE.json configs[1] at full size (4096 environments, 300 substeps per action), through size-independent
+    properties: the run is deterministic (bit-exact repeat), a shard of the global environment ids reproduces its slice
+    bit-exactly, the executed substeps add up in the statistics, flags are consistent, and the edge cases of the call
+    (zero substeps, an all-zero reset mask, a one-environment batch) behave."""
+    from hsr_env_b200.env import BatchedHSREnv
+    from hsr_env_b200.spaces import Box
+    from hsr_env_b200.util import GoalSpec
+    from scenarios import BLOCK_HI, BLOCK_LO, GOAL_HI, GOAL_LO
+
+    goals = [GoalSpec(Box(BLOCK_LO, BLOCK_HI), Box(GOAL_LO, GOAL_HI), .05)]
+    n = 4096
+    gen = torch.Generator().manual_seed(11)
+    acts = [torch.rand(n, 2, generator=gen) * 2 - 1 for _ in range(2)]
+
+    def run(n_envs, off):
+        env = BatchedHSREnv("c2_push.hsrb", goals, n_envs=n_envs, device="cuda:0", seed=9, env_id_offset=off)
+        env.reset()
+        s0 = env.stats()
+        res = []
+        done = None
+        for a in acts:
+            if done is not None:
+                env.reset(mask=done)
+            obs, reward, done, info = env.step(a[off:off + n_envs])
+            res.append((obs.cpu().numpy(), done.cpu().numpy(), info["substeps_taken"].cpu().numpy(), reward.cpu().numpy()))
+        s1 = env.stats()
+        return env, res, s1["substeps"] - s0["substeps"]
+
+    env, a, nsub = run(n, 0)
+    _, b, _ = run(n, 0)
+    e2, c, _ = run(1024, 2048)
+    for (oa, da, ta, ra), (ob, db, tb, rb) in zip(a, b):
+        assert np.array_equal(oa, ob) and np.array_equal(da, db) and np.array_equal(ta, tb)      # deterministic
+    for (oa, da, ta, ra), (oc, dc, tc, rc) in zip(a, c):
+        assert np.array_equal(oa[2048:3072], oc) and np.array_equal(ta[2048:3072], tc)           # shard = slice
+    taken = sum(int(t.sum()) for _, _, t, _ in a)
+    assert taken == nsub                                                                          # statistics add up
+    for o, d, t, r in a:
+        assert np.all(np.isfinite(o)) and np.all((t >= 1) & (t <= 300))
+        assert np.array_equal(r > 0, d.astype(bool)) and np.all(t[~d.astype(bool)] == 300)       # early exit only on success
+        q = o[:, 5:9]
+        assert np.allclose(np.linalg.norm(q, axis=1), 1, atol=1e-5)                              # unit quaternions
+    # zero substeps: the observation is the current state, nothing is taken
+    qpos, qvel, _, _ = env.get_state()
+    h = env  # steps=0 goes through the C ABI directly (the Python front-end maps 0 to the default: `steps or ...`, hsr/env.py:117)
+    import ctypes
+    from hsr_env_b200 import lib as L
+    o0 = torch.empty(n, env.obs_dim, device="cuda:0"); tk = torch.full((n,), -1, dtype=torch.int32, device="cuda:0")
+    L.check(h._lib.hsrb_step(h._h, L.ptr(acts[0].cuda().contiguous()), 0, L.ptr(o0), None, None, None, L.ptr(tk), None, h._stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(o0, torch.cat([qpos, qvel], dim=1)) and int(tk.abs().sum()) == 0
+    # an all-zero mask resets nothing
+    before = [t.clone() for t in env.get_state()]
+    env.reset(mask=torch.zeros(n, dtype=torch.bool))
+    after = env.get_state()
+    assert torch.allclose(before[0], after[0], atol=1e-6) and torch.equal(before[1], after[1])
+    env.close(); e2.close()
+    # a one-environment batch equals environment 0 of the big one
+    e1 = BatchedHSREnv("c2_push.hsrb", goals, n_envs=1, device="cuda:0", seed=9, env_id_offset=0)
+    e1.reset()
+    o1, *_ = e1.step(acts[0][:1])
+    assert np.array_equal(o1.cpu().numpy()[0], a[0][0][0])
+    e1.close()
