@@ -148,7 +148,7 @@ HSRB_DECL_G(4) HSRB_DECL_G(8) HSRB_DECL_G(16) HSRB_DECL_G(32)
 
 #define HSRB_DEFINE_G(G)                                                                                               \
   cudaError_t hsrb_prepare_step_##G(size_t smem, int* bps) {                                                           \
-    cudaError_t e = cudaFuncSetAttribute(hsrb_step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaError_t e = cudaFuncSetAttribute(hsrb_step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); /* per function, shared by all handles */ \
     if (e != cudaSuccess) return e;                                                                                    \
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, hsrb_step_kernel<G>, 32, smem);                          \
   }                                                                                                                    \

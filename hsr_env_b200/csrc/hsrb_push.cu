@@ -4,7 +4,7 @@
 
 template <int G, int NV>
 static cudaError_t prepare_t(size_t smem, int threads, int* bps) {
-  cudaError_t e = cudaFuncSetAttribute(hsrb_push_kernel<G, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(hsrb_push_kernel<G, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per function, not per handle: handles with different layouts share it
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, hsrb_push_kernel<G, NV>, threads, smem);
 }
