@@ -124,6 +124,15 @@ inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) !=
 inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) == mask; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::tl_warp->bar(mask).wait(); }
 inline void __syncthreads() { emu::tl_block->all->wait(); }
+inline int __syncthreads_or(int p) {
+  emu::Block& b = *emu::tl_block;
+  b.all->wait();
+  if (threadIdx.x == 0) b.vote.store(0);
+  b.all->wait();
+  if (p) b.vote.fetch_add(1);
+  b.all->wait();
+  return b.vote.load() != 0;
+}
 inline int __syncthreads_and(int p) {
   emu::Block& b = *emu::tl_block;
   b.all->wait();
