@@ -262,7 +262,6 @@ def run_gpu(args):
     for k in range(e2e_steps):
         mask_dev.copy_(out["done"], non_blocking=True)            # H2D: which environments the caller resets
         env.reset(mask=mask_dev)
-        torch.cuda.current_stream(dev).synchronize()
         env.step_host(act_host[k], out=out)                       # H2D ctrl, kernel, D2H obs/reward/done/taken, sync
     torch.cuda.synchronize(dev)
     e2e_secs = D.max_over_ranks(time.perf_counter() - t0, dev)

@@ -1512,12 +1512,29 @@ HSR_HD void substep(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   HSR_PHASE(w, g, PH_EULER);
 }
 
-// all(in_range(block_i, goal, geofence)) on the body positions of the last forward pass
-// (HSREnv.in_range / distance_between, /root/reference/hsr/env.py:137-147,231-232; strict <)
+// all(in_range(*goal)) on the body positions of the last forward pass
+// (HSREnv.step / in_range / distance_between, /root/reference/hsr/env.py:126,137-147,231-232; strict <).
+// ngoal == 0: the env_wrapper form (every block within `geofence` of the goal point);
+// otherwise the list of GoalSpecs: endpoints are body positions, the per-environment goal point or fixed points.
+template <typename T>
+HSR_HD V3<GT> goal_endpoint(const EnvCfg<T>& cfg, const WS<T>& w, int code) {
+  if (code >= 0) return ld3(w.xpos + 3 * code);
+  if (code == GOAL_EP_POINT) return mk<GT>((GT)w.mocap[0], (GT)w.mocap[1], (GT)w.mocap[2]);
+  const T* p = cfg.fixed_pt[-2 - code];
+  return mk<GT>((GT)p[0], (GT)p[1], (GT)p[2]);
+}
 template <typename T>
 HSR_HD bool goal_reached(const ModelT<T>& m, const EnvCfg<T>& cfg, const WS<T>& w) {
-  if (!cfg.has_goal || m.nblock == 0) return false;
+  if (!cfg.has_goal) return false;
   bool all = true;
+  if (cfg.ngoal > 0) {
+    for (int k = 0; k < cfg.ngoal; k++) {
+      V3<GT> d = goal_endpoint(cfg, w, cfg.goal_a[k]) - goal_endpoint(cfg, w, cfg.goal_b[k]);
+      all = all && (sqrt(dot(d, d)) < (GT)cfg.goal_dist[k]);
+    }
+    return all;
+  }
+  if (m.nblock == 0) return false;
   for (int k = 0; k < m.nblock; k++) {
     const GT* p = w.xpos + 3 * m.block_body[k];
     GT dx = p[0] - (GT)w.mocap[0], dy = p[1] - (GT)w.mocap[1], dz = p[2] - (GT)w.mocap[2];
@@ -1608,30 +1625,40 @@ HSR_HDC void reset_lane0(const ModelT<T>& m, const EnvCfg<T>& cfg, WS<T>& w, uin
   for (int i = 0; i < m.nv; i++) { w.qvel[i] = 0; w.warm[i] = 0; }
   for (int i = 0; i < m.nu; i++) w.ctrl[i] = 0;
   for (int k = 0; k < 3; k++) w.mocap[k] = m.mocap_pos0[k];
-  if (!cfg.has_goal) return;
   uint32_t r[4];
   uint32_t k0 = (uint32_t)seed, k1 = env_id, c2 = (uint32_t)(seed >> 32);
-  philox4x32_10(episode, 0, c2, 0, k0, k1, r);
-  for (int k = 0; k < 3; k++) w.mocap[k] = (T)uniform32(r[k], (float)cfg.goal_lo[k], (float)cfg.goal_hi[k]);
-  for (int b = 0; b < m.nblock && cfg.has_block; b++) {
-    int body = m.block_body[b];
-    int a = m.jnt_qposadr[m.body_jntadr[body]];
-    float s[4];
-    for (int tries = 0; tries < 16; tries++) {
-      philox4x32_10(episode, 1 + b * 16 + tries, c2, 0, k0, k1, r);
-      for (int k = 0; k < 4; k++) s[k] = uniform32(r[k], (float)cfg.block_lo[k], (float)cfg.block_hi[k]);
-      bool ok = true;
-      if (cfg.min_sep > 0)
-        for (int o = 0; o < b; o++) {
-          int ao = m.jnt_qposadr[m.body_jntadr[m.block_body[o]]];
-          T dx = (T)s[0] - w.qpos[ao], dy = (T)s[1] - w.qpos[ao + 1];
-          if (dx * dx + dy * dy < cfg.min_sep * cfg.min_sep) ok = false;
-        }
-      if (ok) break;
+  if (cfg.has_goal) {
+    philox4x32_10(episode, 0, c2, 0, k0, k1, r);
+    for (int k = 0; k < 3; k++) w.mocap[k] = (T)uniform32(r[k], (float)cfg.goal_lo[k], (float)cfg.goal_hi[k]);
+    for (int b = 0; b < m.nblock && cfg.has_block; b++) {
+      int body = m.block_body[b];
+      int a = m.jnt_qposadr[m.body_jntadr[body]];
+      float s[4];
+      for (int tries = 0; tries < 16; tries++) {
+        philox4x32_10(episode, 1 + b * 16 + tries, c2, 0, k0, k1, r);
+        for (int k = 0; k < 4; k++) s[k] = uniform32(r[k], (float)cfg.block_lo[k], (float)cfg.block_hi[k]);
+        bool ok = true;
+        if (cfg.min_sep > 0)
+          for (int o = 0; o < b; o++) {
+            int ao = m.jnt_qposadr[m.body_jntadr[m.block_body[o]]];
+            T dx = (T)s[0] - w.qpos[ao], dy = (T)s[1] - w.qpos[ao + 1];
+            if (dx * dx + dy * dy < cfg.min_sep * cfg.min_sep) ok = false;
+          }
+        if (ok) break;
+      }
+      w.qpos[a] = (T)s[0]; w.qpos[a + 1] = (T)s[1];
+      w.qpos[a + 3] = w.qpos[a + 4] = w.qpos[a + 5] = w.qpos[a + 6] = 0;
+      w.qpos[a + 3 + cfg.qidx0] = (T)s[2]; w.qpos[a + 3 + cfg.qidx1] = (T)s[3];
     }
-    w.qpos[a] = (T)s[0]; w.qpos[a + 1] = (T)s[1];
-    w.qpos[a + 3] = w.qpos[a + 4] = w.qpos[a + 5] = w.qpos[a + 6] = 0;
-    w.qpos[a + 3 + cfg.qidx0] = (T)s[2]; w.qpos[a + 3 + cfg.qidx1] = (T)s[3];
+  }
+  // HSREnv.new_state (/root/reference/hsr/env.py:149-156): qpos slices of the joints that have a start space,
+  // draw block 4096 + 2 s + (0, 1) of the environment's stream (independent of the goal / block draws above; applied last, as new_state is)
+  for (int s = 0; s < cfg.nstart; s++) {
+    const int a = cfg.start_adr[s], wd = cfg.start_width[s];
+    for (int k = 0; k < wd; k++) {
+      if ((k & 3) == 0) philox4x32_10(episode, 4096 + 2 * s + (k >> 2), c2, 0, k0, k1, r);
+      w.qpos[a + k] = (T)uniform32(r[k & 3], (float)cfg.start_lo[s][k], (float)cfg.start_hi[s][k]);
+    }
   }
 }
 

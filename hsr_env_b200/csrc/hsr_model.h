@@ -79,16 +79,32 @@ enum { NP_PLANE_BOX = 0, NP_PLANE_CONVEX = 1, NP_BOX_BOX = 2, NP_CONVEX_CONVEX =
   X(mocap_pos0, 1, 3)
 
 // Environment-level configuration: the goal / block spaces and geofence of the reference's
-// env_wrapper (/root/reference/hsr/util.py:53-74) in the form App. C #2 of SURVEY.md defines.
+// env_wrapper (/root/reference/hsr/util.py:53-74) in the form App. C #2 of SURVEY.md defines, the general
+// list-of-GoalSpec form of HSREnv (/root/reference/hsr/env.py:126,137-147,161-172) and the per-joint start spaces
+// of HSREnv.new_state (/root/reference/hsr/env.py:149-156).
+#define HSRB_MAXGOAL 4     // GoalSpecs in the general form
+#define HSRB_MAXFIXED 4    // fixed (ndarray) goal endpoints beside the sampled point
+#define HSRB_MAXSTART 8    // joints with a start space
+enum { GOAL_EP_POINT = -1 };   // endpoint codes: >= 0 body id, -1 the per-environment goal point (mocap_pos), -2-k fixed point k
 template <typename T>
 struct EnvCfg {
   int has_goal;        // 0: goals=None (README run before the first reset): never done
   int has_block;       // 0: no block-space: blocks reset to their qpos0 pose
   int qidx0, qidx1;    // which quaternion components block-space dims 2,3 drive
-  T goal_lo[3], goal_hi[3];
+  T goal_lo[3], goal_hi[3];   // the sampled goal point (a 3-d Space endpoint; lo == hi for an ndarray) -> mocap_pos
   T block_lo[4], block_hi[4];
   T geofence;
   T min_sep;           // >0: rejection-sample block (x,y) so that blocks start at least this far apart
+  // general form: success = all_k |pos(a_k) - pos(b_k)| < dist_k.  ngoal == 0: the env_wrapper form above
+  // (every block within `geofence` of the goal point).
+  int ngoal;
+  int goal_a[HSRB_MAXGOAL], goal_b[HSRB_MAXGOAL];
+  T goal_dist[HSRB_MAXGOAL];
+  T fixed_pt[HSRB_MAXFIXED][3];
+  // start spaces: qpos[adr .. adr+width) ~ U[lo, hi] at reset (width 1, or 7 for a free joint)
+  int nstart;
+  int start_adr[HSRB_MAXSTART], start_width[HSRB_MAXSTART];
+  T start_lo[HSRB_MAXSTART][7], start_hi[HSRB_MAXSTART][7];
 };
 
 template <typename T>

@@ -61,7 +61,6 @@ struct hsrb {
   float *d_ctrl = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   unsigned char* d_done = nullptr;
   int* d_taken = nullptr;
-  cudaStream_t host_stream = nullptr;
   long long launches = 0;
   // fast path (hsrb_push.cuh): sliding base + at most one free box
   PushInfo fast;
@@ -170,6 +169,9 @@ int configure_fast(hsrb* h) {
   return 0;
 }
 
+// the fast kernel tests the env_wrapper-form goal only (one block against the goal point)
+bool use_fast(const hsrb* h) { return h->fast_ok && h->path != 1 && h->cfg.ngoal == 0; }
+
 KArgs base_args(hsrb* h) {
   KArgs a;
   memset(&a, 0, sizeof(a));
@@ -180,7 +182,7 @@ KArgs base_args(hsrb* h) {
 }
 
 int run(hsrb* h, KArgs& a, void* stream) {
-  if (a.mode == MODE_STEP && h->fast_ok && h->path != 1) {
+  if (a.mode == MODE_STEP && use_fast(h)) {
     int rc = configure_fast(h);
     if (rc) return rc;
     a.ws_bytes = h->fast_ws;
@@ -264,7 +266,6 @@ int hsrb_create(const void* model_blob, size_t bytes, int n_envs, int device, ui
   CUH(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * ST_COUNT));
   CUH(cudaMemset(h->d_episode, 0, sizeof(unsigned) * (size_t)h->n));
   CUH(cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * ST_COUNT));
-  CUH(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
   // state after load = mj_resetData: qpos0, zero velocities (MjSim(model), mujoco_env.py:34)
   {
     std::vector<float> row(h->S, 0.f);
@@ -291,7 +292,7 @@ int hsrb_set_path(hsrb_t* h, int path) {
   if (path < 0 || path > 2) return fail(-1, "path must be 0 (auto), 1 (general kernel) or 2 (fast kernel)");
   if (path == 2 && !h->fast_ok) return fail(-3, "fast path not available for this model: %s", h->fast_why);
   h->path = path;
-  return h->fast_ok && path != 1 ? 2 : 1;
+  return use_fast(h) ? 2 : 1;
 }
 
 int hsrb_destroy(hsrb_t* h) {
@@ -299,7 +300,6 @@ int hsrb_destroy(hsrb_t* h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_fast_tab); cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_episode); cudaFree(h->d_stats);
   cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_taken);
-  if (h->host_stream) cudaStreamDestroy(h->host_stream);
   delete h;
   return 0;
 }
@@ -334,9 +334,53 @@ int hsrb_set_goals(hsrb_t* h, const float* goal_lohi, const float* block_lohi, f
   EnvCfg<float>& c = h->cfg;
   c.has_goal = goal_lohi ? 1 : 0;
   c.has_block = block_lohi ? 1 : 0;
+  c.ngoal = 0;
   c.qidx0 = qidx0; c.qidx1 = qidx1; c.geofence = geofence; c.min_sep = min_sep;
   for (int k = 0; k < 3; k++) { c.goal_lo[k] = goal_lohi ? goal_lohi[k] : 0.f; c.goal_hi[k] = goal_lohi ? goal_lohi[3 + k] : 0.f; }
   for (int k = 0; k < 4; k++) { c.block_lo[k] = block_lohi ? block_lohi[k] : 0.f; c.block_hi[k] = block_lohi ? block_lohi[4 + k] : 0.f; }
+  return 0;
+}
+
+int hsrb_set_goal_list(hsrb_t* h, int ngoal, const int32_t* a_codes, const int32_t* b_codes, const float* distance,
+                       const float* point_lohi, const float* fixed_pts, int nfixed) {
+  if (!h) return fail(-1, "null handle");
+  if (ngoal < 0 || ngoal > HSRB_MAXGOAL) return fail(-1, "at most %d GoalSpecs", HSRB_MAXGOAL);
+  if (nfixed < 0 || nfixed > HSRB_MAXFIXED) return fail(-1, "at most %d fixed goal points", HSRB_MAXFIXED);
+  if (ngoal > 0 && (!a_codes || !b_codes || !distance)) return fail(-1, "goal list arrays are NULL");
+  EnvCfg<float>& c = h->cfg;
+  for (int k = 0; k < ngoal; k++) {
+    const int codes[2] = {a_codes[k], b_codes[k]};
+    for (int e = 0; e < 2; e++) {
+      if (codes[e] >= h->hm.m.nbody) return fail(-1, "goal %d: body id %d out of range", k, codes[e]);
+      if (codes[e] < -1 - nfixed) return fail(-1, "goal %d: fixed point %d not given", k, -2 - codes[e]);
+    }
+  }
+  c.ngoal = ngoal;
+  c.has_goal = ngoal > 0 ? 1 : 0;
+  c.has_block = 0;
+  for (int k = 0; k < ngoal; k++) { c.goal_a[k] = a_codes[k]; c.goal_b[k] = b_codes[k]; c.goal_dist[k] = distance[k]; }
+  for (int k = 0; k < 3; k++) {
+    c.goal_lo[k] = point_lohi ? point_lohi[k] : h->hm.m.mocap_pos0[k];
+    c.goal_hi[k] = point_lohi ? point_lohi[3 + k] : h->hm.m.mocap_pos0[k];
+  }
+  for (int k = 0; k < nfixed; k++) for (int i = 0; i < 3; i++) c.fixed_pt[k][i] = fixed_pts[3 * k + i];
+  return 0;
+}
+
+int hsrb_set_starts(hsrb_t* h, int nstart, const int32_t* qpos_adr, const int32_t* width, const float* lo, const float* hi) {
+  if (!h) return fail(-1, "null handle");
+  if (nstart < 0 || nstart > HSRB_MAXSTART) return fail(-1, "at most %d joints with a start space", HSRB_MAXSTART);
+  if (nstart > 0 && (!qpos_adr || !width || !lo || !hi)) return fail(-1, "start arrays are NULL");
+  EnvCfg<float>& c = h->cfg;
+  for (int s = 0; s < nstart; s++) {
+    if (width[s] != 1 && width[s] != 7) return fail(-1, "start %d: width must be 1 (slide / hinge) or 7 (free joint)", s);
+    if (qpos_adr[s] < 0 || qpos_adr[s] + width[s] > h->hm.m.nq) return fail(-1, "start %d: qpos slice out of range", s);
+  }
+  c.nstart = nstart;
+  for (int s = 0; s < nstart; s++) {
+    c.start_adr[s] = qpos_adr[s]; c.start_width[s] = width[s];
+    for (int k = 0; k < 7; k++) { c.start_lo[s][k] = k < width[s] ? lo[7 * s + k] : 0.f; c.start_hi[s][k] = k < width[s] ? hi[7 * s + k] : 0.f; }
+  }
   return 0;
 }
 
@@ -361,8 +405,9 @@ int hsrb_step(hsrb_t* h, const float* ctrl, int nsubsteps, float* obs, float* re
 }
 
 int hsrb_step_host(hsrb_t* h, const float* ctrl_host, int nsubsteps, float* obs_host, float* reward_host,
-                   uint8_t* done_host, int32_t* taken_host) {
+                   uint8_t* done_host, int32_t* taken_host, void* stream) {
   if (!h) return fail(-1, "null handle");
+  if (!ctrl_host && h->hm.m.nu > 0) return fail(-1, "ctrl_host is NULL");
   CU(cudaSetDevice(h->device));
   const int n = h->n, nu = h->hm.m.nu, nobs = h->hm.m.nq + h->hm.m.nv;
   if (!h->d_obs) {
@@ -372,7 +417,10 @@ int hsrb_step_host(hsrb_t* h, const float* ctrl_host, int nsubsteps, float* obs_
     CU(cudaMalloc(&h->d_done, (size_t)n));
     CU(cudaMalloc(&h->d_taken, sizeof(int) * (size_t)n));
   }
-  cudaStream_t s = h->host_stream;
+  // Everything is enqueued on the CALLER's stream, behind whatever the caller launched there before (hsrb_reset,
+  // hsrb_set_state, a previous step), so no cross-stream ordering is left to the caller; the call returns after the
+  // device->host copies have completed.
+  cudaStream_t s = (cudaStream_t)stream;
   if (nu > 0) CU(cudaMemcpyAsync(h->d_ctrl, ctrl_host, sizeof(float) * (size_t)n * nu, cudaMemcpyHostToDevice, s));
   int rc = hsrb_step(h, h->d_ctrl, nsubsteps, h->d_obs, h->d_reward, h->d_done, nullptr, h->d_taken, nullptr, s);
   if (rc) return rc;
@@ -462,7 +510,7 @@ int hsrb_launch_info(hsrb_t* h, int* out4) {  // out4: 6 ints
   CU(cudaSetDevice(h->device));
   int rc = configure(h);
   if (rc) return rc;
-  if (h->fast_ok && h->path != 1) {
+  if (use_fast(h)) {
     rc = configure_fast(h);
     if (rc) return rc;
     out4[0] = h->fast_lanes; out4[1] = (int)h->fast_ws; out4[2] = h->fast_bps * (h->fast_threads / h->fast_lanes); out4[3] = h->fast_grid;

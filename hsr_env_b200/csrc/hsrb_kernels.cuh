@@ -86,16 +86,16 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
       taken = 1;
     } else if (a.mode == MODE_RESET) {
       // MujocoEnv.reset + HSREnv.reset_model (mujoco_env.py:83-85, env.py:158-177) for the masked environments
+      // environments outside the mask keep their state bit for bit (only their observation is emitted)
       if (!a.mask || a.mask[env]) {
         if (g.lane == 0) {
           unsigned ep = a.episode[env];
           a.episode[env] = ep + 1;
           reset_lane0(a.m, a.cfg, w, a.seed, (uint32_t)(a.env_off + (unsigned long long)env), ep);
+          kinematics_lane0(a.m, w);  // sim.forward(): normalises free-joint quaternions in qpos
         }
         g.sync();
       }
-      if (g.lane == 0) kinematics_lane0(a.m, w);  // sim.forward(): normalises free-joint quaternions in qpos
-      g.sync();
     } else {  // MODE_FORWARD: body positions of the current state (data.get_body_xpos, env.py:144,180,184)
       if (g.lane == 0) kinematics_lane0(a.m, w);
       g.sync();

@@ -131,43 +131,122 @@ class BatchedHSREnv:
         self._time_steps = 0
         self._geofence = 0.0
         self._parse_goal_specs()
+        self._push_starts()
 
     # ------------------------------------------------------------------ goals
+    def _body_id(self, name: str) -> int:
+        """Fused-body id of a body name (a body without joints is fused into its parent by the loader: its position is
+        the parent's frame plus a constant offset, which only the renderer needs)."""
+        names = list(self.model.names.get("body", []))
+        if name in names:
+            return names.index(name)
+        if name == "block" and len(self.model.block_body):     # hsr/__init__.py:12 vs env.py:58 (SURVEY App. C #9)
+            return int(self.model.block_body[0])
+        raise KeyError(f"no moving body named {name!r} in the model (bodies: {names})")
+
     def _parse_goal_specs(self):
-        """GoalSpec(a=block_space, b=goal_space, distance=geofence) (hsr/util.py:70-74) -> kernel config, with the
-        meaning SURVEY.md App. C #2 fixes: block-space (x, y, quat[i0], quat[i1]) is written into every block's
-        free joint at reset, goal-space is the 3-d goal point (mocap_pos), success = all blocks within
-        ``distance`` of the goal.  The ``hsr/__init__.py:12`` form GoalSpec('block', array, d) is accepted too."""
+        """``goals`` -> kernel configuration.  Two forms:
+
+        * the env_wrapper form (hsr/util.py:70-74): ONE GoalSpec(a=4-d block-space Box, b=3-d goal-space Box, distance)
+          with the meaning SURVEY.md App. C #2 fixes: block-space (x, y, quat[i0], quat[i1]) is written into every
+          block's free joint at reset, goal-space is the goal point (mocap_pos), success = all blocks within
+          ``distance`` of it;
+        * the general form of HSREnv (hsr/env.py:126,137-147,161-172): a list of up to four GoalSpec(a, b, distance)
+          whose endpoints are body names (``data.get_body_xpos``), ndarrays or 3-d Spaces (sampled at reset);
+          success = all(in_range(*g)).  As in the reference, at most one endpoint can be a Space (``mocap_pos[:] =
+          concatenate(...)`` holds one point, hsr/env.py:169-172); further ndarray endpoints are fixed points.
+          Callable endpoints (hsr/env.py:139-140) would have to run after every substep inside the kernel: they are
+          accepted by the single-environment ``HSREnv.in_range`` only."""
         self._goal_lohi = None
         self._block_lohi = None
+        self._goal_list = None
         if not self.goals_specs:
             return
-        if len(self.goals_specs) != 1:
-            raise NotImplementedError("exactly one GoalSpec (the env_wrapper form) is supported")
-        a, b, dist = self.goals_specs[0]
-        self._geofence = float(dist)
-        if _is_space(b):
-            self._goal_lohi = np.concatenate([np.asarray(b.low, np.float32), np.asarray(b.high, np.float32)])
-        else:
-            b = np.asarray(b, np.float32).reshape(3)
-            self._goal_lohi = np.concatenate([b, b])
-        assert self._goal_lohi.shape == (6,), "goal space must be 3-d"
-        if _is_space(a):
-            self._block_lohi = np.concatenate([np.asarray(a.low, np.float32), np.asarray(a.high, np.float32)])
-            assert self._block_lohi.shape == (8,), "block space must be 4-d"
-        elif a is None or isinstance(a, str):
-            self._block_lohi = None  # blocks start where the model puts them (qpos0)
-        else:
-            raise NotImplementedError("GoalSpec.a must be a 4-d Box (block-space), a body name or None")
+        specs = [GoalSpec(*g) for g in self.goals_specs]
+        a, b, dist = specs[0]
+        wrapper_form = len(specs) == 1 and (a is None or (_is_space(a) and np.asarray(a.low).size == 4))
+        if wrapper_form:
+            self._geofence = float(dist)
+            if _is_space(b):
+                self._goal_lohi = np.concatenate([np.asarray(b.low, np.float32), np.asarray(b.high, np.float32)])
+            else:
+                b = np.asarray(b, np.float32).reshape(3)
+                self._goal_lohi = np.concatenate([b, b])
+            assert self._goal_lohi.shape == (6,), "goal space must be 3-d"
+            if a is not None:
+                self._block_lohi = np.concatenate([np.asarray(a.low, np.float32), np.asarray(a.high, np.float32)])
+                assert self._block_lohi.shape == (8,), "block space must be 4-d"
+            return
+        if len(specs) > 4:
+            raise NotImplementedError("at most four GoalSpecs")
+        codes, dists, fixed, point = [], [], [], None
+        for g in specs:
+            pair = []
+            for x in (g.a, g.b):
+                if isinstance(x, str):
+                    pair.append(self._body_id(x))
+                elif _is_space(x):
+                    if point is not None:
+                        raise ValueError("only one GoalSpec endpoint can be a Space: mocap_pos holds one point (hsr/env.py:169-172)")
+                    lo, hi = np.asarray(x.low, np.float32).reshape(3), np.asarray(x.high, np.float32).reshape(3)
+                    point = np.concatenate([lo, hi])
+                    pair.append(-1)
+                elif callable(x):
+                    raise NotImplementedError("callable GoalSpec endpoints cannot run inside the action kernel; "
+                                              "use body names / arrays / Spaces, or HSREnv.in_range on the single-env facade")
+                else:
+                    v = np.asarray(x, np.float32).reshape(3)
+                    if point is None and not any(_is_space(y) for h in specs for y in (h.a, h.b)):
+                        point = np.concatenate([v, v])        # the ndarray endpoint that goes to mocap_pos
+                        pair.append(-1)
+                    else:
+                        if len(fixed) >= 4:
+                            raise NotImplementedError("at most four fixed goal points beside the sampled one")
+                        fixed.append(v)
+                        pair.append(-2 - (len(fixed) - 1))
+            codes.append(pair)
+            dists.append(float(g.distance))
+        self._geofence = dists[0]
+        self._goal_list = dict(a=np.asarray([c[0] for c in codes], np.int32), b=np.asarray([c[1] for c in codes], np.int32),
+                               dist=np.asarray(dists, np.float32), point=point,
+                               fixed=np.asarray(fixed, np.float32).reshape(-1, 3))
 
     def _push_goals(self, active: bool):
         fp = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        if self._goal_list is not None:
+            g = self._goal_list
+            _lib.check(self._lib.hsrb_set_goal_list(
+                self._h, len(g["a"]) if active else 0, g["a"].ctypes.data_as(ip), g["b"].ctypes.data_as(ip),
+                g["dist"].ctypes.data_as(fp), g["point"].ctypes.data_as(fp) if g["point"] is not None else None,
+                g["fixed"].ctypes.data_as(fp) if len(g["fixed"]) else None, len(g["fixed"])))
+            return
         g = self._goal_lohi if active else None
         blk = self._block_lohi
         _lib.check(self._lib.hsrb_set_goals(
             self._h, g.ctypes.data_as(fp) if g is not None else None,
             blk.ctypes.data_as(fp) if blk is not None else None, self._geofence, self._min_sep,
             self._qidx[0], self._qidx[1]))
+
+    def _push_starts(self):
+        """``starts`` (hsr/env.py:149-156) -> per-joint lo / hi table of the reset kernel (Philox draws keyed on the
+        global environment id: reproducible, independent of batch size and sharding)."""
+        names = list(self.model.names.get("joint", []))
+        adr, width, lo, hi = [], [], [], []
+        for joint, space in self.starts.items():
+            assert _is_space(space), f"starts[{joint!r}] must be a Space (hsr/env.py:152)"
+            j = names.index(joint)
+            w = 7 if int(self.model.jnt_type[j]) == 0 else 1
+            l, h = np.zeros(7, np.float32), np.zeros(7, np.float32)
+            l[:w] = np.asarray(space.low, np.float32).reshape(w); h[:w] = np.asarray(space.high, np.float32).reshape(w)
+            adr.append(int(self.model.jnt_qposadr[j])); width.append(w); lo.append(l); hi.append(h)
+        fp = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        adr, width = np.asarray(adr, np.int32), np.asarray(width, np.int32)
+        lo, hi = np.ascontiguousarray(lo, np.float32).reshape(-1, 7), np.ascontiguousarray(hi, np.float32).reshape(-1, 7)
+        n = len(adr)
+        _lib.check(self._lib.hsrb_set_starts(self._h, n, adr.ctypes.data_as(ip) if n else None, width.ctypes.data_as(ip) if n else None,
+                                             lo.ctypes.data_as(fp) if n else None, hi.ctypes.data_as(fp) if n else None))
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -197,29 +276,7 @@ class BatchedHSREnv:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_reset(self._h, _lib.ptr(mask), _lib.ptr(obs), self._stream()))
-            if self.starts:
-                obs = self._apply_starts(mask)
         return self._observation(obs)
-
-    def _apply_starts(self, mask):
-        """new_state (hsr/env.py:149-156): qpos slices of named joints drawn from their start spaces."""
-        qpos, qvel, _, _ = self.get_state()
-        names = self.model.names.get("joint", [])
-        for joint, space in self.starts.items():
-            j = names.index(joint)
-            a = int(self.model.jnt_qposadr[j])
-            w = 7 if int(self.model.jnt_type[j]) == 0 else 1
-            draw = np.stack([np.asarray(space.sample(), np.float32).reshape(w) for _ in range(self.n_envs)])
-            draw = torch.from_numpy(draw).to(self.device)
-            if mask is None:
-                qpos[:, a:a + w] = draw
-            else:
-                sel = mask.bool()
-                qpos[sel, a:a + w] = draw[sel]
-        self.set_state(qpos, qvel)
-        self.body_xpos()   # sim.forward() (hsr/env.py:176): normalises the free-joint quaternions in qpos
-        qpos, qvel, _, _ = self.get_state()
-        return torch.cat([qpos, qvel], dim=1)
 
     def step(self, action: torch.Tensor, steps: Optional[int] = None):
         """HSREnv.step (hsr/env.py:115-135) for every environment: one kernel launch."""
@@ -238,17 +295,31 @@ class BatchedHSREnv:
         info = {"log count": {"success": done_b}, "substeps_taken": taken, "bad_state": bad}
         return self._observation(obs), reward, done_b, info
 
-    def step_host(self, action: np.ndarray, steps: Optional[int] = None, out=None):
-        """Same call with HOST buffers (numpy / pinned torch CPU tensors), copies inside: the end-to-end path."""
+    def step_host(self, action, steps: Optional[int] = None, out=None):
+        """Same call with HOST buffers (numpy / pinned torch CPU tensors), copies inside: the end-to-end path.  Runs on
+        torch's current stream, i.e. after any reset / set_state / step issued before it."""
         if self._obs_type == "openai":
             raise NotImplementedError("step_host returns the kernel's qpos|qvel observation; use step() for obs_type='openai'")
         steps = steps or self.steps_per_action
+        if isinstance(action, torch.Tensor):
+            if action.dtype != torch.float32 or not action.is_contiguous() or action.numel() != self.n_envs * self.nu or action.is_cuda:
+                action = action.detach().to("cpu", torch.float32).reshape(self.n_envs, self.nu).contiguous()
+        else:
+            action = np.ascontiguousarray(action, np.float32).reshape(self.n_envs, self.nu)
         if out is None:
             out = dict(obs=np.empty((self.n_envs, self.state_dim), np.float32), reward=np.empty(self.n_envs, np.float32),
                        done=np.empty(self.n_envs, np.uint8), taken=np.empty(self.n_envs, np.int32))
+        want = dict(obs=((self.n_envs, self.state_dim), "float32"), reward=((self.n_envs,), "float32"),
+                    done=((self.n_envs,), "uint8"), taken=((self.n_envs,), "int32"))
+        for k, (shape, dt) in want.items():
+            buf = out[k]
+            got_dt = str(buf.dtype).replace("torch.", "")
+            if tuple(buf.shape) != shape or got_dt != dt:
+                raise ValueError(f"step_host: out[{k!r}] must be {dt}{list(shape)}, got {got_dt}{list(buf.shape)}")
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_step_host(self._h, _lib.ptr(action), int(steps), _lib.ptr(out["obs"]),
-                                                _lib.ptr(out["reward"]), _lib.ptr(out["done"]), _lib.ptr(out["taken"])))
+                                                _lib.ptr(out["reward"]), _lib.ptr(out["done"]), _lib.ptr(out["taken"]),
+                                                self._stream()))
         self._time_steps += 1
         return out
 

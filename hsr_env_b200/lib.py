@@ -22,9 +22,12 @@ SIGNATURES = {
     "hsrb_config": (c_int, [c_void_p, c_int, c_int, c_int]),
     "hsrb_set_path": (c_int, [c_void_p, c_int]),
     "hsrb_set_goals": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), c_float, c_float, c_int, c_int]),
+    "hsrb_set_goal_list": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_float), POINTER(c_float),
+                                   POINTER(c_float), c_int]),
+    "hsrb_set_starts": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_float), POINTER(c_float)]),
     "hsrb_reset": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsrb_step": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 7),
-    "hsrb_step_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hsrb_step_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsrb_get_state": (c_int, [c_void_p] + [c_void_p] * 5),
     "hsrb_set_state": (c_int, [c_void_p] + [c_void_p] * 5),
     "hsrb_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -31,7 +31,10 @@ int hsrb_dims(hsrb_t* h, int* nq, int* nv, int* nu, int* nbody, int* nblock);
 
 /* Tuning knobs, valid before the first reset/step: lanes of a warp per environment (0 = auto from n_envs;
  * 4, 8, 16 or 32) and the contact / constraint-row capacities (0 = model default; MuJoCo's nconmax/njmax,
- * /root/reference/hsr/models/world.xml:44). */
+ * /root/reference/hsr/models/world.xml:44).  The capacities apply to the general kernel; the fast kernel of the
+ * sliding-base family has a fixed capacity of 8 contacts (48 contact rows + 2 limit rows) per environment, which the
+ * one-block model cannot exceed by more than a transient (4 floor corners + hull contacts); an overflow sets bit 0 of
+ * bad_state on either path. */
 int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max);
 
 /* Kernel selection: 0 = auto (the fast kernel (hsrb_push.cuh) when the model is a sliding base with at most
@@ -45,6 +48,24 @@ int hsrb_set_path(hsrb_t* h, int path);
 int hsrb_set_goals(hsrb_t* h, const float* goal_lohi_host, const float* block_lohi_host, float geofence,
                    float min_sep, int qidx0, int qidx1);
 
+/* The general list-of-GoalSpec form of HSREnv              /root/reference/hsr/env.py:126,137-147,161-172
+ * success = all_k |pos(a_k) - pos(b_k)| < distance_k, evaluated after every substep.  Endpoint codes: >= 0 a (fused)
+ * body id (a body-name endpoint, data.get_body_xpos), -1 the per-environment goal point (a Space endpoint sampled at
+ * reset from point_lohi = {lo[3], hi[3]}, or an ndarray endpoint with lo == hi; written to mocap_pos as env.py:169-172
+ * does; NULL = the model's mocap_pos0), -2-k fixed point k of fixed_pts[nfixed][3] (further ndarray endpoints).
+ * ngoal <= 4, nfixed <= 4.  Replaces any hsrb_set_goals configuration (and vice versa); ngoal = 0 means goals=None.
+ * Callable endpoints (env.py:139-140) cannot run inside a kernel: the Python front-end rejects them in batched mode.
+ * Models of the sliding-base family run the general kernel when this form is active. */
+int hsrb_set_goal_list(hsrb_t* h, int ngoal, const int32_t* a_codes_host, const int32_t* b_codes_host,
+                       const float* distance_host, const float* point_lohi_host, const float* fixed_pts_host, int nfixed);
+
+/* HSREnv.new_state: per-joint start spaces                   /root/reference/hsr/env.py:149-156
+ * qpos[qpos_adr[s] .. + width[s]) ~ U[lo[s], hi[s]] at every reset (width 1, or 7 for a free joint; lo / hi are
+ * [nstart][7]), drawn inside the reset kernel from the environment's Philox stream (key = seed, GLOBAL env id; counter =
+ * episode, draw block 4096 + 2 s): reproducible and independent of batch size / sharding.  nstart <= 8; 0 clears. */
+int hsrb_set_starts(hsrb_t* h, int nstart, const int32_t* qpos_adr_host, const int32_t* width_host, const float* lo_host,
+                    const float* hi_host);
+
 /* MujocoEnv.reset + HSREnv.reset_model                      mujoco_env.py:83-85, env.py:158-177
  * mask[N] (NULL = all): environments to reset.  obs[N, nq+nv] (nullable) receives the new observation. */
 int hsrb_reset(hsrb_t* h, const uint8_t* mask, float* obs, void* stream);
@@ -57,9 +78,12 @@ int hsrb_step(hsrb_t* h, const float* ctrl, int nsubsteps, float* obs, float* re
               int32_t* substeps_taken, uint8_t* bad_state, void* stream);
 
 /* Same call with HOST buffers (the way the reference's caller holds its numpy arrays, hsr/control.py:48-63):
- * copies ctrl host->device, steps, copies obs/reward/done/substeps device->host and synchronises. */
+ * copies ctrl host->device, steps, copies obs/reward/done/substeps device->host, all enqueued on `stream` - the
+ * CALLER's stream, so the step is ordered after whatever the caller launched there before (hsrb_reset,
+ * hsrb_set_state, a previous step) - and returns after synchronising that stream.  ctrl_host must hold [N, nu]
+ * float32, the outputs [N, nq+nv] float32, [N] float32, [N] uint8, [N] int32 (nullable). */
 int hsrb_step_host(hsrb_t* h, const float* ctrl_host, int nsubsteps, float* obs_host, float* reward_host,
-                   uint8_t* done_host, int32_t* substeps_taken_host);
+                   uint8_t* done_host, int32_t* substeps_taken_host, void* stream);
 
 /* sim.get_state / sim.set_state (+ qacc_warmstart, which MuJoCo keeps outside MjSimState)   env.py:69,150,175
  * qpos[N,nq] qvel[N,nv] qacc_warm[N,nv] mocap_pos[N,3]; NULL pointers are skipped. */

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
@@ -108,9 +109,28 @@ int run(Handle* h, int n, int nsub, int nthreads, const double* qpos, const doub
 
 template <typename T> void set_cfg(EnvCfg<T>& c, int has_goal, int has_block, const double* goal_lohi, const double* block_lohi,
                                    double geofence, double min_sep, int qidx0, int qidx1) {
+  c.ngoal = 0;
   c.has_goal = has_goal; c.has_block = has_block; c.qidx0 = qidx0; c.qidx1 = qidx1; c.geofence = (T)geofence; c.min_sep = (T)min_sep;
   for (int k = 0; k < 3; k++) { c.goal_lo[k] = (T)goal_lohi[k]; c.goal_hi[k] = (T)goal_lohi[3 + k]; }
   for (int k = 0; k < 4; k++) { c.block_lo[k] = (T)block_lohi[k]; c.block_hi[k] = (T)block_lohi[4 + k]; }
+}
+
+template <typename T> void set_goal_list(EnvCfg<T>& c, const ModelT<T>& m, int ngoal, const int* a, const int* b, const double* dist,
+                                         const double* point_lohi, const double* fixed, int nfixed) {
+  c.ngoal = ngoal; c.has_goal = ngoal > 0; c.has_block = 0;
+  for (int k = 0; k < ngoal; k++) { c.goal_a[k] = a[k]; c.goal_b[k] = b[k]; c.goal_dist[k] = (T)dist[k]; }
+  for (int k = 0; k < 3; k++) {
+    c.goal_lo[k] = point_lohi ? (T)point_lohi[k] : m.mocap_pos0[k];
+    c.goal_hi[k] = point_lohi ? (T)point_lohi[3 + k] : m.mocap_pos0[k];
+  }
+  for (int k = 0; k < nfixed; k++) for (int i = 0; i < 3; i++) c.fixed_pt[k][i] = (T)fixed[3 * k + i];
+}
+template <typename T> void set_starts(EnvCfg<T>& c, int n, const int* adr, const int* width, const double* lo, const double* hi) {
+  c.nstart = n;
+  for (int s = 0; s < n; s++) {
+    c.start_adr[s] = adr[s]; c.start_width[s] = width[s];
+    for (int k = 0; k < 7; k++) { c.start_lo[s][k] = k < width[s] ? (T)lo[7 * s + k] : T(0); c.start_hi[s][k] = k < width[s] ? (T)hi[7 * s + k] : T(0); }
+  }
 }
 
 }  // namespace
@@ -125,6 +145,7 @@ void* hsrp_create(const void* blob, size_t bytes) {
     delete h;
     return nullptr;
   }
+  memset(&h->cfgd, 0, sizeof(h->cfgd)); memset(&h->cfgf, 0, sizeof(h->cfgf));
   double z3[6] = {0, 0, 0, 0, 0, 0}, z4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   set_cfg(h->cfgd, 0, 0, z3, z4, 0.0, 0.0, 0, 2);
   set_cfg(h->cfgf, 0, 0, z3, z4, 0.0, 0.0, 0, 2);
@@ -150,6 +171,19 @@ void hsrp_set_goals(void* hv, int has_goal, int has_block, const double* goal_lo
   Handle* h = (Handle*)hv;
   set_cfg(h->cfgd, has_goal, has_block, goal_lohi, block_lohi, geofence, min_sep, qidx0, qidx1);
   set_cfg(h->cfgf, has_goal, has_block, goal_lohi, block_lohi, geofence, min_sep, qidx0, qidx1);
+}
+
+// mirrors of hsrb_set_goal_list / hsrb_set_starts (include/hsrb.h)
+void hsrp_set_goal_list(void* hv, int ngoal, const int* a, const int* b, const double* dist, const double* point_lohi,
+                        const double* fixed, int nfixed) {
+  Handle* h = (Handle*)hv;
+  set_goal_list(h->cfgd, h->md.m, ngoal, a, b, dist, point_lohi, fixed, nfixed);
+  set_goal_list(h->cfgf, h->mf.m, ngoal, a, b, dist, point_lohi, fixed, nfixed);
+}
+void hsrp_set_starts(void* hv, int n, const int* adr, const int* width, const double* lo, const double* hi) {
+  Handle* h = (Handle*)hv;
+  set_starts(h->cfgd, n, adr, width, lo, hi);
+  set_starts(h->cfgf, n, adr, width, lo, hi);
 }
 
 // Step n environments by up to nsub substeps each (teacher-forced from the given states).

@@ -43,6 +43,9 @@ class CpuPort:
         lib.hsrp_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [_dp] * 8 + [
             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(ctypes.c_int), _dp,
             ctypes.POINTER(ctypes.c_longlong)]
+        _ip = ctypes.POINTER(ctypes.c_int)
+        lib.hsrp_set_goal_list.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip, _ip, _dp, _dp, _dp, ctypes.c_int]
+        lib.hsrp_set_starts.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip, _ip, _dp, _dp]
         lib.hsrp_reset.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, _dp, _dp]
         self.lib = lib
         blob = model.to_blob()
@@ -66,6 +69,19 @@ class CpuPort:
         g = np.ascontiguousarray(np.zeros(6) if goal_lohi is None else np.asarray(goal_lohi, float).reshape(6))
         b = np.ascontiguousarray(np.zeros(8) if block_lohi is None else np.asarray(block_lohi, float).reshape(8))
         self.lib.hsrp_set_goals(self.h, int(has), int(block_lohi is not None), _p(g), _p(b), float(geofence), float(min_sep), qidx[0], qidx[1])
+
+    def set_goal_list(self, a, b, dist, point_lohi=None, fixed=None):
+        """mirror of hsrb_set_goal_list: endpoint codes >= 0 body id, -1 the goal point, -2-k fixed point k"""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32); dist = np.ascontiguousarray(dist, float)
+        pl = None if point_lohi is None else np.ascontiguousarray(point_lohi, float).reshape(6)
+        fx = np.zeros((0, 3)) if fixed is None else np.ascontiguousarray(fixed, float).reshape(-1, 3)
+        self.lib.hsrp_set_goal_list(self.h, len(a), _p(a, ctypes.c_int), _p(b, ctypes.c_int), _p(dist), _p(pl) if pl is not None else None,
+                                    _p(fx) if len(fx) else None, len(fx))
+
+    def set_starts(self, adr, width, lo, hi):
+        adr = np.ascontiguousarray(adr, np.int32); width = np.ascontiguousarray(width, np.int32)
+        lo = np.ascontiguousarray(lo, float).reshape(-1, 7); hi = np.ascontiguousarray(hi, float).reshape(-1, 7)
+        self.lib.hsrp_set_starts(self.h, len(adr), _p(adr, ctypes.c_int), _p(width, ctypes.c_int), _p(lo), _p(hi))
 
     def step(self, qpos, qvel, warm, ctrl, mocap=None, nsub=1, use_float=False, nthreads=1, debug=False):
         qpos = np.ascontiguousarray(np.atleast_2d(qpos), float)
