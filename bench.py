@@ -337,7 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = auto)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast", "wpe"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -17,10 +17,12 @@
 #include <string>
 
 #include "../../include/hsrb.h"
-#include "hsrb_push.cuh"
+#include "hsrb_wpe.cuh"
 
 cudaError_t hsrb_push_prepare(int G, int nv, size_t smem, int threads, int* bps);
 cudaError_t hsrb_push_launch(int G, int nv, const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s);
+cudaError_t hsrb_wpe_prepare(size_t smem, int threads, int* bps);
+cudaError_t hsrb_wpe_launch(const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s);
 
 namespace {
 
@@ -72,6 +74,10 @@ struct hsrb {
   int fast_lanes = 8, fast_threads = 0, fast_grid = 0, fast_bps = 0;
   unsigned fast_ws = 0;
   char fast_why[128] = "";
+  // warp-per-environment kernel of the same family (hsrb_wpe.cuh)
+  bool wpe_ok = false, wpe_configured = false;
+  int wpe_threads = 0, wpe_grid = 0, wpe_bps = 0;
+  unsigned wpe_ws = 0;
 };
 
 namespace {
@@ -169,8 +175,40 @@ int configure_fast(hsrb* h) {
   return 0;
 }
 
-// the fast kernel tests the env_wrapper-form goal only (one block against the goal point)
+// the fast kernels test the env_wrapper-form goal only (one block against the goal point)
 bool use_fast(const hsrb* h) { return h->fast_ok && h->path != 1 && h->cfg.ngoal == 0; }
+// which of the two: path 3 = warp-per-environment kernel, 2 = lock-step kernel; 0 (auto) = the lock-step kernel unless
+// HSRB_FAST_KERNEL=wpe (measured on B200, round 2: 4096 envs 45.5 M substeps/s lock-step vs 40.6 M warp-per-environment,
+// 131072 envs 62.3 M vs 61.4 M)
+bool use_wpe(const hsrb* h) {
+  if (!use_fast(h) || !h->wpe_ok) return false;
+  if (h->path == 3) return true;
+  if (h->path == 2) return false;
+  const char* o = getenv("HSRB_FAST_KERNEL");
+  return o && o[0] == 'w';
+}
+
+int configure_wpe(hsrb* h) {
+  if (h->wpe_configured) return 0;
+  h->wpe_ws = (unsigned)wpe::slice_bytes();
+  const size_t tail = wpe::shared_tail(h->dm);
+  // one warp per environment; all environments resident in one wave when they fit (warps per block = n / SMs),
+  // otherwise the most warps shared memory and the register file hold, and a grid-stride loop over the environments
+  int wpb = (h->n + h->num_sm - 1) / h->num_sm;
+  if (wpb < 1) wpb = 1;
+  if (wpb > WPE_MAXWARPS) wpb = WPE_MAXWARPS;
+  if (const char* o = getenv("HSRB_WPE_WPB")) { int v = atoi(o); if (v >= 1 && v <= WPE_MAXWARPS) wpb = v; }   // experiments
+  while (wpb > 1 && (size_t)h->wpe_ws * wpb + tail > 227 * 1024) wpb--;
+  h->wpe_threads = 32 * wpb;
+  const size_t smem = (size_t)h->wpe_ws * wpb + tail;
+  CU(hsrb_wpe_prepare(smem, h->wpe_threads, &h->wpe_bps));
+  if (h->wpe_bps < 1) return fail(-3, "warp-per-environment kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+  const int need = (h->n + wpb - 1) / wpb;
+  const int cap = h->wpe_bps * h->num_sm;
+  h->wpe_grid = need < cap ? need : cap;
+  h->wpe_configured = true;
+  return 0;
+}
 
 KArgs base_args(hsrb* h) {
   KArgs a;
@@ -182,6 +220,16 @@ KArgs base_args(hsrb* h) {
 }
 
 int run(hsrb* h, KArgs& a, void* stream) {
+  if (a.mode == MODE_STEP && use_wpe(h)) {
+    int rc = configure_wpe(h);
+    if (rc) return rc;
+    a.ws_bytes = h->wpe_ws;
+    a.m.ncon_max = WPE_MAXCON; a.m.nefc_max = WPE_MAXROW;
+    const size_t smem = (size_t)h->wpe_ws * (h->wpe_threads / 32) + wpe::shared_tail(h->dm);
+    CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+  }
   if (a.mode == MODE_STEP && use_fast(h)) {
     int rc = configure_fast(h);
     if (rc) return rc;
@@ -282,6 +330,9 @@ int hsrb_create(const void* model_blob, size_t bytes, int n_envs, int device, ui
     if (e2 == cudaSuccess) e2 = cudaMemcpy(h->d_fast_tab, h->fast_tab.tab.data(), h->fast_tab.bytes(), cudaMemcpyHostToDevice);
     if (e2 != cudaSuccess) { int rc_ = fail(-2, "fast-path tables: %s", cudaGetErrorString(e2)); hsrb_destroy(h); return rc_; }
     h->fast_tab.point(h->fast, h->d_fast_tab);
+    int nbg = 0;
+    for (int gi = 0; gi < h->hm.m.ngeom; gi++) nbg += h->hm.m.geom_body[gi] == h->fast.block_body ? 1 : 0;
+    h->wpe_ok = nbg <= WPE_MAXBG && h->hm.m.npair <= WPE_MAXPAIR && h->hm.m.ngeom <= WPE_MAXGEOM;
   }
   *out = h;
   return 0;
@@ -289,10 +340,11 @@ int hsrb_create(const void* model_blob, size_t bytes, int n_envs, int device, ui
 
 int hsrb_set_path(hsrb_t* h, int path) {
   if (!h) return fail(-1, "null handle");
-  if (path < 0 || path > 2) return fail(-1, "path must be 0 (auto), 1 (general kernel) or 2 (fast kernel)");
-  if (path == 2 && !h->fast_ok) return fail(-3, "fast path not available for this model: %s", h->fast_why);
+  if (path < 0 || path > 3) return fail(-1, "path must be 0 (auto), 1 (general kernel), 2 (lock-step fast kernel) or 3 (warp-per-environment fast kernel)");
+  if (path >= 2 && !h->fast_ok) return fail(-3, "fast path not available for this model: %s", h->fast_why);
+  if (path == 3 && !h->wpe_ok) return fail(-3, "warp-per-environment kernel not available for this model");
   h->path = path;
-  return use_fast(h) ? 2 : 1;
+  return use_wpe(h) ? 3 : (use_fast(h) ? 2 : 1);
 }
 
 int hsrb_destroy(hsrb_t* h) {
@@ -323,6 +375,7 @@ int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max) {
   if (nefc_max > 0) h->dm.nefc_max = h->hm.m.nefc_max = nefc_max;
   h->configured = false;
   h->fast_configured = false;
+  h->wpe_configured = false;
   CU(cudaSetDevice(h->device));
   return configure(h);
 }
@@ -510,6 +563,13 @@ int hsrb_launch_info(hsrb_t* h, int* out4) {  // out4: 6 ints
   CU(cudaSetDevice(h->device));
   int rc = configure(h);
   if (rc) return rc;
+  if (use_wpe(h)) {
+    rc = configure_wpe(h);
+    if (rc) return rc;
+    out4[0] = 32; out4[1] = (int)h->wpe_ws; out4[2] = h->wpe_bps * (h->wpe_threads / 32); out4[3] = h->wpe_grid;
+    out4[4] = 3; out4[5] = h->wpe_threads;
+    return 0;
+  }
   if (use_fast(h)) {
     rc = configure_fast(h);
     if (rc) return rc;

@@ -1,0 +1,1020 @@
+// Warp-per-environment action kernel of the "sliding base + at most one free box" models (README block-push:
+// --use-dof slide_x slide_y, --n-blocks 0/1; BASELINE.json configs[0], [1] and [3]).
+//
+// Same substep as hsrb_push.cuh / the general kernel, laid out for occupancy instead of for
+// register residency:
+//   * ONE WARP owns one environment; a block is up to 28 independent warps (no block barrier after the table copy),
+//     so every environment advances at its own pace: a substep costs its own Newton iterations and its own narrowphase
+//     queries, not those of the slowest environment of a lock-stepped block (measured on the bench workload: mean 1.3
+//     Newton iterations per environment-substep, 5.3 for the slowest of 32).
+//   * <= 72 registers per thread (28 warps = 28 environments resident per SM, 7 per scheduler: the dependent chains
+//     of one warp are hidden behind the other six instead of behind a barrier).  State, poses, contacts, constraint
+//     rows, solver vectors and the portal of the convex-convex query live in the warp's 5 KB slice of shared memory;
+//     registers only hold what a phase is working on.
+//   * Lane roles: lane k = candidate pair k (cull), box corner k (plane-box), hull vertices k, k+32, ... (support
+//     scan), constraint row r = k, k+32 (Jacobian products), constraint group k (one contact or one joint limit: cone
+//     state, line-search coefficients), and dof k & 7 with row stripe k >> 3 (gradient, Hessian row, Cholesky row).
+//   * Joint limits are ordinary one-row groups, rows are packed (condim rows per contact).
+//
+// Replaces the loop over sim.step() in HSREnv.step (/root/reference/hsr/env.py:115-135).
+#pragma once
+#include "hsrb_push.cuh"
+
+#define WPE_MAXCON 8                       // contacts per environment (as the lock-step kernel)
+#define WPE_GROUPS (WPE_MAXCON + 2)        // constraint groups: contacts + the two slide limits
+#define WPE_SLOTS (6 * WPE_GROUPS)         // six row slots per group (rows >= the group's dimension are zero rows)
+#define WPE_MAXROW (6 * WPE_MAXCON + 2)    // MuJoCo's nefc at capacity
+#define WPE_MAXBG 2                        // geoms riding on the block
+#define WPE_MAXGEOM 24                     // capacities of the fixed shared-memory layout (c2_push: 18 geoms, 21 pairs)
+#define WPE_MAXPAIR 24
+#ifndef WPE_MAXWARPS
+#define WPE_MAXWARPS 28
+#endif
+
+namespace wpe {
+
+// Fixed layouts: every field sits at a compile-time offset from ONE base address, so a shared-memory access is an
+// LDS / STS with an immediate offset and no table of pointers lives in registers (the first version carried ~50 of them
+// and spilled through local memory on every phase).
+struct alignas(16) Tab {   // block-shared model tables (one copy per block)
+  double gbase[WPE_MAXGEOM * 3];
+  double gmatw[WPE_MAXGEOM * 9];
+  double pairc[WPE_MAXPAIR * PUSH_PAIRC];
+  float ghalf[WPE_MAXGEOM * 3];
+  float geom_rbound[WPE_MAXGEOM];
+  float geom_size[WPE_MAXGEOM * 3];
+  float pair_friction[WPE_MAXPAIR * 5];
+  float geom_mat[WPE_MAXGEOM * 9];
+  float geom_aabb[WPE_MAXGEOM * 3];
+  int gmove[WPE_MAXGEOM], geom_type[WPE_MAXGEOM], geom_vertadr[WPE_MAXGEOM], geom_vertnum[WPE_MAXGEOM];
+  int pair_geom1[WPE_MAXPAIR], pair_geom2[WPE_MAXPAIR], pair_func[WPE_MAXPAIR], pair_condim[WPE_MAXPAIR];
+  float pair_sr[WPE_MAXPAIR], pair_sb[WPE_MAXPAIR];   // sign of the pair's contact Jacobian on the robot / block dofs
+};
+
+struct alignas(16) Slice {   // per-warp (= per-environment) slice
+  double xb[4], Rb[10], bmat[9 * WPE_MAXBG], gpos[WPE_MAXGEOM * 3], portal[46], mres[8];
+  float qpos[12], qvel[8], warm[8], mocap[4], ctrl[4];
+  float gaabb[WPE_MAXGEOM * 3];
+  float qs[8], as[8], x[8], qfc[8], srch[8];
+  float con_dist[WPE_MAXCON], con_pos[WPE_MAXCON * 3], con_frame[WPE_MAXCON * 9];
+  int con_pair[WPE_MAXCON], con_adr[WPE_MAXCON], wi[WI_COUNT];
+  float J[WPE_SLOTS * 8];                                       // 32-byte Jacobian rows
+  float Dr[64], aref[64], rsc[64], jar[64], jv[64], f[64], wrow[64];   // per row slot (rsc: mu on row 0, friction[j-1] on row j)
+  float PQ[16 * WPE_GROUPS], wpq[24], L[64];
+  float sep[4 * WPE_MAXPAIR];
+};
+
+__host__ __device__ inline size_t slice_bytes() { return sizeof(Slice); }
+// block-shared tail after the slices: the tables, then the hull vertices as float4
+__host__ __device__ inline size_t shared_tail(const ModelT<float>& m) { return sizeof(Tab) + (size_t)m.nvert * 16 + 16; }
+
+}  // namespace wpe
+
+// kernel + device routines: only in the translation unit that owns them (hsrb_wpe.cu, the emulated build)
+#if defined(HSRB_WPE_IMPL)
+namespace wpe {
+
+typedef V3<double> V3d;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// world orientation of a geom: table entry (static / robot geoms) or the per-substep product for block geoms
+__device__ __forceinline__ const double* geom_mat(const Tab& t, const Slice& s, int gi, int gb0) {
+  return t.gmove[gi] == 2 ? s.bmat + 9 * (gi - gb0) : t.gmatw + 9 * gi;
+}
+
+// support point of geom gi along d (world frame); hull scan in fp32 over the 32 lanes, everything else in double
+// (same arithmetic as hsr::support_d)
+__device__ __noinline__ V3d support(const Tab& t, const Slice& s, const float* verts4, int gi, int gb0, V3d d) {
+  const double* R = geom_mat(t, s, gi, gb0);
+  const V3d dl = multv(R, d);
+  const int type = t.geom_type[gi];
+  const float* sz = t.geom_size + 3 * gi;
+  V3d res;
+  if (type == GEOM_BOX) {
+    res = mk<double>(dl.x >= 0 ? (double)sz[0] : -(double)sz[0], dl.y >= 0 ? (double)sz[1] : -(double)sz[1],
+                     dl.z >= 0 ? (double)sz[2] : -(double)sz[2]);
+  } else if (type == GEOM_CYLINDER) {
+    const double n = sqrt(dl.x * dl.x + dl.y * dl.y);
+    res = mk<double>(0, 0, dl.z >= 0 ? (double)sz[1] : -(double)sz[1]);
+    if (n > 1e-15) { res.x = dl.x / n * (double)sz[0]; res.y = dl.y / n * (double)sz[0]; }
+  } else {
+    const DevGrp<32> gw;
+    const float* v4 = verts4 + 4 * t.geom_vertadr[gi];
+    const int bi = hull_scan4(reinterpret_cast<const float4*>(v4), t.geom_vertnum[gi], (float)dl.x, (float)dl.y, (float)dl.z, gw);
+    res = mk<double>((double)v4[4 * bi], (double)v4[4 * bi + 1], (double)v4[4 * bi + 2]);
+  }
+  return ld3(s.gpos + 3 * gi) + mulv(R, res);
+}
+
+// portal vertex k of the warp's scratch: 9 doubles  v = v1 - v2 | v1 (on geom 1) | v2 (on geom 2)
+__device__ __forceinline__ V3d pv(const Slice& s, int k) { return ld3(s.portal + 9 * k); }
+__device__ __forceinline__ void pcopy(Slice& s, int dst, int src) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 9) s.portal[9 * dst + lane] = s.portal[9 * src + lane];
+  __syncwarp();
+}
+
+// Minkowski portal refinement (libccd ccdMPRPenetration as used by mjc_Convex), the decisions and the arithmetic of
+// hsr::mpr_penetration_inl, restructured around ONE support evaluation site (a state machine) with the portal in shared
+// memory: a few hundred instructions of code and a handful of live doubles instead of five 9-double vertices in
+// registers.  `sep`: cached separating direction of the pair (see hsr::mpr_penetration_inl).  Result -> s.mres.
+__device__ __noinline__ bool mpr(const Tab& t, Slice& s, const float* verts4, int g1, int g2, int gb0, double tol,
+                                 int max_iter, float* sep) {
+  double* const out7 = s.mres;   // depth, direction, position (written by lane 0)
+  const int lane = threadIdx.x & 31;
+  enum { S_CACHE = 0, S_V1, S_V2, S_DISCOVER, S_REFINE, S_PENETRATE };
+  const double eps = DBL_EPSILON;
+  V3d v0 = ld3(s.gpos + 3 * g1) - ld3(s.gpos + 3 * g2);
+  if (lane == 0) {
+    st3(s.portal + 3, ld3(s.gpos + 3 * g1)); st3(s.portal + 6, ld3(s.gpos + 3 * g2));
+  }
+  if (fabs(v0.x) < eps && fabs(v0.y) < eps && fabs(v0.z) < eps) v0.x += eps * 10;
+  if (lane == 0) st3(s.portal, v0);
+  __syncwarp();
+  int state = S_V1;
+  V3d d;
+  if (sep && sep[3] == 1.f) {
+    state = S_CACHE;
+    d = normalized(mk<double>((double)sep[0], (double)sep[1], (double)sep[2]));
+  } else {
+    d = normalized(-v0);
+  }
+  int guard = 0, it = 0;
+#pragma unroll 1
+  while (true) {
+    // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along d
+    const V3d a1 = support(t, s, verts4, g1, gb0, d);
+    const V3d a2 = support(t, s, verts4, g2, gb0, -d);
+    const V3d v4 = a1 - a2;
+    __syncwarp();
+    if (lane == 0) { st3(s.portal + 36, v4); st3(s.portal + 39, a1); st3(s.portal + 42, a2); }
+    __syncwarp();
+    double dt = dot(v4, d);
+    bool enter_refine = false;
+    if (state == S_CACHE) {
+      if (dt < 0 && !is_zero(dt)) return false;            // the cached direction still separates the pair
+      if (lane == 0) sep[3] = 0.f;
+      state = S_V1;
+      d = normalized(-v0);
+      continue;
+    }
+    if (state <= S_DISCOVER) {
+      if (is_zero(dt) || dt < 0) {                         // origin outside the support plane: disjoint (or touching)
+        if (dt < 0 && !is_zero(dt) && sep && lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = 1.f; }
+        return false;
+      }
+    }
+    if (state == S_V1) {
+      pcopy(s, 1, 4);
+      d = cross(v0, v4);
+      if (is_zero(dot(d, d))) {
+        if (fabs(v4.x) < eps && fabs(v4.y) < eps && fabs(v4.z) < eps) return false;
+        const double dep = norm(v4);
+        const V3d dir = v4 * (1.0 / dep), pos = (a1 + a2) * 0.5;
+        if (lane == 0) {
+          out7[0] = dep; out7[1] = dir.x; out7[2] = dir.y; out7[3] = dir.z; out7[4] = pos.x; out7[5] = pos.y; out7[6] = pos.z;
+          if (sep) sep[3] = 2.f;
+        }
+        __syncwarp();
+        return true;
+      }
+      d = normalized(d);
+      state = S_V2;
+      continue;
+    }
+    if (state == S_V2) {
+      pcopy(s, 2, 4);
+      const V3d v1 = pv(s, 1);
+      d = normalized(cross(v1 - v0, v4 - v0));
+      if (dot(d, v0) > 0) {                                // swap v1 and v2
+        pcopy(s, 2, 1); pcopy(s, 1, 4);
+        d = -d;
+      }
+      state = S_DISCOVER; guard = 0;
+      continue;
+    }
+    if (state == S_DISCOVER) {
+      pcopy(s, 3, 4);
+      const V3d v1 = pv(s, 1), v2 = pv(s, 2);
+      bool cont = false;
+      dt = dot(cross(v1, v4), v0);
+      if (dt < 0 && !is_zero(dt)) { pcopy(s, 2, 3); cont = true; }
+      if (!cont) {
+        dt = dot(cross(v4, v2), v0);
+        if (dt < 0 && !is_zero(dt)) { pcopy(s, 1, 3); cont = true; }
+      }
+      guard++;
+      if (cont && guard < 64) {
+        const V3d w1 = pv(s, 1), w2 = pv(s, 2);
+        d = normalized(cross(w1 - v0, w2 - v0));
+        continue;
+      }
+      state = S_REFINE; guard = 0;
+      enter_refine = true;
+    }
+    if (state == S_REFINE && !enter_refine) {
+      if (!(is_zero(dt) || dt > 0)) {                      // the new support point does not pass the origin: disjoint
+        if (sep && lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = 1.f; }
+        return false;
+      }
+    }
+    if (state == S_PENETRATE || (state == S_REFINE && !enter_refine)) {
+      // reach_tol + expand are common to the refinement and the penetration loop
+      const V3d v1 = pv(s, 1), v2 = pv(s, 2), v3 = pv(s, 3);
+      const double d1 = dt - dot(v1, d), d2 = dt - dot(v2, d), d3 = dt - dot(v3, d);
+      const double mn = fmin(d1, fmin(d2, d3));
+      const bool reach = ccd_eq(mn, tol) || mn < tol;
+      if (state == S_REFINE) {
+        if (reach) return false;
+      } else if (reach || it > max_iter) {
+        V3d q;
+        const double dd2 = origin_tri_dist2(v1, v2, v3, q);
+        const double dep = sqrt(dd2);
+        if (is_zero(dep)) return false;
+        const V3d dir = q * (1.0 / norm(q));
+        double b0 = dot(cross(v1, v2), v3), b1 = dot(cross(v3, v2), v0), b2 = dot(cross(v0, v1), v3), b3 = dot(cross(v2, v1), v0);
+        double sm = b0 + b1 + b2 + b3;
+        if (is_zero(sm) || sm < 0) {
+          b0 = 0; b1 = dot(cross(v2, v3), d); b2 = dot(cross(v3, v1), d); b3 = dot(cross(v1, v2), d);
+          sm = b1 + b2 + b3;
+        }
+        const double inv = 1.0 / sm;
+        const double* P = s.portal;
+        const V3d p1 = (ld3(P + 3) * b0 + ld3(P + 12) * b1 + ld3(P + 21) * b2 + ld3(P + 30) * b3) * inv;
+        const V3d p2 = (ld3(P + 6) * b0 + ld3(P + 15) * b1 + ld3(P + 24) * b2 + ld3(P + 33) * b3) * inv;
+        const V3d pos = (p1 + p2) * 0.5;
+        if (lane == 0) {
+          out7[0] = dep; out7[1] = dir.x; out7[2] = dir.y; out7[3] = dir.z; out7[4] = pos.x; out7[5] = pos.y; out7[6] = pos.z;
+          if (sep) sep[3] = 2.f;
+        }
+        __syncwarp();
+        return true;
+      }
+      // expand the portal with v4
+      const V3d v4v0 = cross(v4, v0);
+      int repl;
+      if (dot(v1, v4v0) > 0) repl = dot(v2, v4v0) > 0 ? 1 : 3;
+      else repl = dot(v3, v4v0) > 0 ? 2 : 1;
+      pcopy(s, repl, 4);
+      if (state == S_REFINE) guard++; else it++;
+    }
+    // ---- next direction: the portal's normal
+    {
+      const V3d v1 = pv(s, 1), v2 = pv(s, 2), v3 = pv(s, 3);
+      d = normalized(cross(v2 - v1, v3 - v1));
+      if (state == S_REFINE) {
+        const double dv = dot(d, v1);
+        if (is_zero(dv) || dv > 0 || guard >= 256) state = S_PENETRATE;   // the portal encloses the origin ray
+      }
+    }
+  }
+}
+
+}  // namespace wpe
+
+// ---------------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __grid_constant__ KArgs a, const __grid_constant__ PushInfo fi) {
+  HSRB_DYN_SMEM(smem);
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const ModelT<float>& m = a.m;
+  // ---- block-shared: model tables + hull vertices as float4 (one copy per block), after the warps' slices
+  wpe::Tab& tw = *reinterpret_cast<wpe::Tab*>(smem + (size_t)wpb * sizeof(wpe::Slice));
+  float* const v4w = reinterpret_cast<float*>(smem + (size_t)wpb * sizeof(wpe::Slice) + sizeof(wpe::Tab));
+  {
+    const int ng = m.ngeom, np = m.npair;
+    for (int i = threadIdx.x; i < m.nvert * 4; i += blockDim.x) v4w[i] = fi.verts4[i];
+#define TAB_COPY(field, src, n) for (int i = threadIdx.x; i < (n); i += blockDim.x) tw.field[i] = (src)[i];
+    TAB_COPY(gbase, fi.gbase, ng * 3) TAB_COPY(gmatw, fi.gmatw, ng * 9) TAB_COPY(pairc, fi.pairc, np * PUSH_PAIRC)
+    TAB_COPY(ghalf, fi.ghalf, ng * 3) TAB_COPY(geom_rbound, m.geom_rbound, ng)
+    TAB_COPY(geom_size, m.geom_size, ng * 3) TAB_COPY(pair_friction, m.pair_friction, np * 5)
+    TAB_COPY(geom_mat, m.geom_mat, ng * 9) TAB_COPY(geom_aabb, m.geom_aabb, ng * 3)
+    TAB_COPY(gmove, fi.gmove, ng) TAB_COPY(geom_type, m.geom_type, ng)
+    TAB_COPY(geom_vertadr, m.geom_vertadr, ng) TAB_COPY(geom_vertnum, m.geom_vertnum, ng)
+    TAB_COPY(pair_geom1, m.pair_geom1, np) TAB_COPY(pair_geom2, m.pair_geom2, np)
+    TAB_COPY(pair_func, m.pair_func, np) TAB_COPY(pair_condim, m.pair_condim, np)
+#undef TAB_COPY
+    for (int k = threadIdx.x; k < np; k += blockDim.x) {
+      const int b1 = m.geom_body[m.pair_geom1[k]], b2 = m.geom_body[m.pair_geom2[k]];
+      tw.pair_sr[k] = (float)(b2 == fi.robot_body) - (float)(b1 == fi.robot_body);
+      tw.pair_sb[k] = (float)(b2 == fi.block_body) - (float)(b1 == fi.block_body);
+    }
+    __syncthreads();   // the only block barrier of the kernel
+  }
+  const wpe::Tab& t = tw;
+  const float* const verts4 = v4w;
+  wpe::Slice& s = *reinterpret_cast<wpe::Slice*>(smem + (size_t)wib * sizeof(wpe::Slice));
+  const int NV = fi.nv;
+  const bool HASB = NV == 8;
+  const int nq = m.nq;
+  const float dt = m.timestep;
+  const float scale = 1.0f / (m.meaninertia * (float)(NV > 1 ? NV : 1));
+  const int li = lane & 7, sub = lane >> 3;   // dof owned by this lane, row stripe of this lane
+  int gb0 = m.ngeom;                          // first geom riding on the block
+  for (int i = m.ngeom - 1; i >= 0; i--) if (t.gmove[i] == 2) gb0 = i;
+  const float Mi = li < NV ? fi.Mdiag[li] : 1.0f, dampi = li < NV ? fi.damp[li] : 0.f;
+  const bool use_sep = !(a.opts & 1u);
+
+#pragma unroll 1
+  for (int env = blockIdx.x * wpb + wib; env < a.n; env += gridDim.x * wpb) {
+    // ------------------------------------------------------------------ state -> shared memory
+    {
+      const float* st = a.state + (size_t)env * a.S;
+      if (lane < 12) s.qpos[lane] = (lane < nq) ? st[lane] : 0.f;
+      if (lane < 8) {
+        s.qvel[lane] = lane < NV ? st[nq + lane] : 0.f;
+        s.warm[lane] = lane < NV ? st[nq + NV + lane] : 0.f;
+        s.qfc[lane] = 0.f;
+      }
+      if (lane < 3) s.mocap[lane] = st[nq + 2 * NV + lane];
+      if (lane < 2) s.ctrl[lane] = (a.ctrl && lane < fi.act_n) ? a.ctrl[(size_t)env * m.nu + lane] : 0.f;
+      for (int i = lane; i < WI_COUNT; i += 32) s.wi[i] = 0;
+      for (int i = lane; i < 4 * m.npair; i += 32) s.sep[i] = 0.f;     // no cached separating directions
+      for (int i = lane; i < m.ngeom * 3; i += 32) { s.gpos[i] = t.gbase[i]; s.gaabb[i] = t.ghalf[i]; }
+      if (lane < 3) s.xb[lane] = 0;
+      if (lane < 9) s.Rb[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
+    }
+    int n_iter = 0, n_ls = 0, sumcon = 0, sumefc = 0, kflop = 0, flags = 0, narrow_tot = 0;
+    bool success = false;
+    int taken = 0;
+    __syncwarp();
+
+#pragma unroll 1
+    for (int sb_ = 0; sb_ < a.nsub; sb_++) {
+      // ---------------------------------------------------------------- poses (B.1), geometry in double
+      if (HASB) {
+        double qd[4] = {(double)s.qpos[5], (double)s.qpos[6], (double)s.qpos[7], (double)s.qpos[8]};
+        quatnormalize(qd);   // same rounding as the oracle: the narrowphase decisions downstream are discontinuous in the pose
+        double Rb[9];
+        quat2mat(qd, Rb);
+        __syncwarp();
+        if (lane < 4) s.qpos[5 + lane] = (float)qd[lane];  // MuJoCo normalises qpos in place
+        if (lane < 3) s.xb[lane] = (double)s.qpos[2 + lane];
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 9; k++) s.Rb[k] = Rb[k];
+        }
+        __syncwarp();
+      }
+      {
+        const double q0 = (double)s.qpos[0], q1 = (double)s.qpos[1];
+        for (int gg = lane; gg < m.ngeom; gg += 32) {
+          const int mv = t.gmove[gg];
+          if (mv == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) s.gpos[3 * gg + k] = t.gbase[3 * gg + k] + fi.axisd[0][k] * q0 + fi.axisd[1][k] * q1;
+          } else if (mv == 2) {
+            const double* Rb = s.Rb;
+            const wpe::V3d p = ld3(s.xb) + mulv(Rb, ld3(t.gbase + 3 * gg));
+            st3(s.gpos + 3 * gg, p);
+            mulm(Rb, t.gmatw + 9 * gg, s.bmat + 9 * (gg - gb0));
+            float Rbf[9], Rg[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rbf[k] = (float)Rb[k];
+            mulm(Rbf, t.geom_mat + 9 * gg, Rg);
+            const float* h = t.geom_aabb + 3 * gg;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+              s.gaabb[3 * gg + i] = fabsf(Rg[3 * i]) * h[0] + fabsf(Rg[3 * i + 1]) * h[1] + fabsf(Rg[3 * i + 2]) * h[2];
+          }
+        }
+      }
+      __syncwarp();
+      // ---------------------------------------------------------------- active joint limits: groups 0 .. nlimit-1
+      int nlimit = 0;
+      {
+        bool act = false;
+        float sg = 0.f, Dv = 0.f, ar = 0.f;
+        if (lane < 2 && fi.limited[lane]) {
+          const float q = s.qpos[lane];
+          const float dlo = q - fi.range[lane][0], dhi = fi.range[lane][1] - q;
+          float dist = 0.f;
+          if (dlo < 0) { dist = dlo; sg = 1.f; }
+          else if (dhi < 0) { dist = dhi; sg = -1.f; }
+          if (sg != 0.f) {
+            act = true;
+            const double imp = push::impedance5(fi.lim_imp[lane], (double)dist);
+            const double R = fmax(1e-15, (1 - imp) / imp * fi.lim_diag[lane]);
+            Dv = (float)(1.0 / R);
+            ar = (float)(-fi.lim_b[lane] * (double)(sg * s.qvel[lane]) - fi.lim_k[lane] * imp * (double)dist);
+          }
+        }
+        const unsigned lm = __ballot_sync(FULL, act);
+        nlimit = __popc(lm);
+        if (act) {
+          const int gslot = 6 * __popc(lm & ((1u << lane) - 1u));
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            float4* jp = reinterpret_cast<float4*>(s.J + 8 * (gslot + r));
+            jp[0] = (r == 0) ? make_float4(lane == 0 ? sg : 0.f, lane == 1 ? sg : 0.f, 0.f, 0.f) : z4;
+            jp[1] = z4;
+            s.Dr[gslot + r] = r == 0 ? Dv : 0.f; s.aref[gslot + r] = r == 0 ? ar : 0.f; s.rsc[gslot + r] = r == 0 ? 1.f : 0.f;
+          }
+        }
+      }
+      // ---------------------------------------------------------------- collision (B.3): contacts in pair order
+      int ncon = 0, nefc = nlimit, narrow = 0, npflop = 0;
+#pragma unroll 1
+      for (int base = 0; base < m.npair; base += 32) {
+        const int k = base + lane;
+        bool hit = false;
+        if (k < m.npair) {
+          const int ga = t.pair_geom1[k], gb = t.pair_geom2[k];
+          const V3<float> dp = cvt<float>(ld3(s.gpos + 3 * gb) - ld3(s.gpos + 3 * ga));
+          if (t.geom_type[ga] == GEOM_PLANE) {
+            const double* Ma = t.gmatw + 9 * ga;  // planes are static: world orientation is a table entry
+            hit = dot(dp, mk<float>((float)Ma[2], (float)Ma[5], (float)Ma[8])) <= t.geom_rbound[gb];
+          } else {
+            const float rr = t.geom_rbound[ga] + t.geom_rbound[gb];
+            hit = dot(dp, dp) <= rr * rr;
+            const float* ha = s.gaabb + 3 * ga; const float* hb = s.gaabb + 3 * gb;
+            hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
+          }
+        }
+        unsigned bits = __ballot_sync(FULL, hit);
+#pragma unroll 1
+        while (bits) {
+          const int l = __ffs((int)bits) - 1;
+          bits &= bits - 1;
+          const int pk = base + l;
+          const int func = t.pair_func[pk];
+          const int ga = t.pair_geom1[pk], gb = t.pair_geom2[pk];
+          const int dim = t.pair_condim[pk];
+          narrow++;
+          npflop += func == NP_PLANE_BOX ? 80 : (func == NP_PLANE_CONVEX ? 100 : (func == NP_BOX_BOX ? 500 : 5000));
+          if (func == NP_PLANE_BOX) {
+            // mjc_PlaneBox: one corner per lane; the first four penetrating corners (corner order) become contacts
+            const double* Ma = t.gmatw + 9 * ga;
+            const wpe::V3d n = mk<double>(Ma[2], Ma[5], Ma[8]);
+            const wpe::V3d pb = ld3(s.gpos + 3 * gb);
+            const double dist0 = dot(pb - ld3(s.gpos + 3 * ga), n);
+            const int i = lane;
+            const float* sz = t.geom_size + 3 * gb;
+            const wpe::V3d c = mk<double>((i & 1) ? (double)sz[0] : -(double)sz[0], (i & 2) ? (double)sz[1] : -(double)sz[1],
+                                          (i & 4) ? (double)sz[2] : -(double)sz[2]);
+            const wpe::V3d vec = mulv(wpe::geom_mat(t, s, gb, gb0), c);
+            const double ld = dot(n, vec);
+            const bool pen = i < 8 && !(dist0 + ld > 0 || ld > 0);
+            const unsigned pm = __ballot_sync(FULL, pen);
+            const int rank = __popc(pm & ((1u << i) - 1u));
+            int nh = __popc(pm);
+            if (nh > 4) nh = 4;
+            const int room = WPE_MAXCON - ncon;
+            if (pen && rank < nh && rank < room) {
+              const int slot = ncon + rank;
+              const double dist = dist0 + ld;
+              s.con_pair[slot] = pk; s.con_dist[slot] = (float)dist;
+              st3c(s.con_pos + 3 * slot, pb + vec - n * (dist * 0.5));
+              make_frame(n, s.con_frame + 9 * slot);
+            }
+            if (nh > room) { nh = room; flags |= FLAG_CON_OVERFLOW; }
+            ncon += nh; nefc += nh * dim;
+          } else if (func == NP_CONVEX_CONVEX || func == NP_PLANE_CONVEX) {
+            bool hitc;
+            if (func == NP_PLANE_CONVEX) {
+              const double* Ma = t.gmatw + 9 * ga;
+              const wpe::V3d n = mk<double>(Ma[2], Ma[5], Ma[8]);
+              const wpe::V3d p = wpe::support(t, s, verts4, gb, gb0, -n);
+              const double dist = dot(p - ld3(s.gpos + 3 * ga), n);
+              hitc = dist <= 0;
+              const wpe::V3d pos = p - n * (dist * 0.5);
+              __syncwarp();
+              if (lane == 0) { double* r7 = s.mres; r7[0] = -dist; r7[1] = n.x; r7[2] = n.y; r7[3] = n.z; r7[4] = pos.x; r7[5] = pos.y; r7[6] = pos.z; }
+              __syncwarp();
+            } else {
+              hitc = wpe::mpr(t, s, verts4, ga, gb, gb0, (double)m.mpr_tolerance, m.mpr_iterations, use_sep ? s.sep + 4 * pk : nullptr);
+            }
+            if (hitc) {
+              if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
+              else {
+                if (lane == 0) {
+                  const double* r7 = s.mres;
+                  s.con_pair[ncon] = pk; s.con_dist[ncon] = (float)(-r7[0]);
+                  s.con_pos[3 * ncon] = (float)r7[4]; s.con_pos[3 * ncon + 1] = (float)r7[5]; s.con_pos[3 * ncon + 2] = (float)r7[6];
+                  make_frame(mk<double>(r7[1], r7[2], r7[3]), s.con_frame + 9 * ncon);
+                }
+                ncon++; nefc += dim;
+              }
+            }
+          } else {   // box-box (block against the pan): hsr_core.h, rare
+            WS<float> w;                                // view for hsr::box_box / add_contact
+            w.gpos = s.gpos; w.gaabb = s.gaabb; w.con_dist = s.con_dist; w.con_pos = s.con_pos; w.con_frame = s.con_frame;
+            w.con_pair = s.con_pair; w.con_adr = s.con_adr; w.wi = s.wi; w.sep = nullptr;
+            const DevGrp<32> g;
+            Geom<float> A, B;
+            A.type = GEOM_BOX; B.type = GEOM_BOX; A.verts = B.verts = nullptr; A.nvert = B.nvert = 0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) { A.size[q] = t.geom_size[3 * ga + q]; B.size[q] = t.geom_size[3 * gb + q]; }
+            A.pos = ld3(s.gpos + 3 * ga); B.pos = ld3(s.gpos + 3 * gb);
+            const double* RA = wpe::geom_mat(t, s, ga, gb0); const double* RB = wpe::geom_mat(t, s, gb, gb0);
+#pragma unroll
+            for (int q = 0; q < 9; q++) { A.mat[q] = RA[q]; B.mat[q] = RB[q]; }
+            int nrow_ = nefc;
+            box_box(m, w, g, ncon, nrow_, pk, A, B);   // capacities: the host sets m.ncon_max / m.nefc_max to this kernel's
+            nefc = nrow_;
+            __syncwarp();
+            flags |= s.wi[WI_FLAGS];
+          }
+        }
+      }
+      narrow_tot += narrow;
+      __syncwarp();
+      const int ngrp = nlimit + ncon;
+      const int nslot = 6 * ngrp;
+      sumcon += ncon; sumefc += nefc;
+
+      // ---------------------------------------------------------------- smooth forces (closed form, B.6): dof lanes
+      if (lane < 8) {
+        float q = 0.f;
+        const float v = s.qvel[lane];
+        if (lane < 2) {
+          q = -fi.damp[lane] * v + fi.gq[lane];
+          for (int k = 0; k < fi.act_n; k++) {
+            if (fi.act_dof[k] != lane) continue;
+            float c = s.ctrl[k];
+            if (fi.ctrllimited[k]) c = fminf(fmaxf(c, fi.cr_lo[k]), fi.cr_hi[k]);
+            float fo = fi.kp[k] * c - fi.kp[k] * fi.gear[k] * s.qpos[fi.act_q[k]];
+            if (fi.forcelimited[k]) fo = fminf(fmaxf(fo, fi.fr_lo[k]), fi.fr_hi[k]);
+            q += fi.gear[k] * fo;
+          }
+        } else if (HASB) {
+          if (lane < 5) q = fi.Mdiag[2] * fi.gravity[lane - 2] - fi.damp[lane] * v;
+          else {
+            // free box: -w x (I w) on the body-frame rotational dofs
+            const int i0 = lane - 5, i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+            const float w1 = s.qvel[5 + i1], w2 = s.qvel[5 + i2];
+            q = -(w1 * (fi.Mdiag[5 + i2] * w2) - w2 * (fi.Mdiag[5 + i1] * w1)) - fi.damp[lane] * v;
+          }
+        }
+        s.qs[lane] = q;
+        s.as[lane] = lane < NV ? q / fi.Mdiag[lane] : 0.f;
+      }
+      // ---------------------------------------------------------------- constraint rows: one contact per group lane (B.4/B.5)
+      int gdim = 0;
+      if (lane < nlimit) gdim = 1;
+      else if (lane < ngrp) {
+        const int c = lane - nlimit;
+        const int pk = s.con_pair[c];
+        gdim = t.pair_condim[pk];
+        const float sr = t.pair_sr[pk], sbk = t.pair_sb[pk];
+        const float* fr = s.con_frame + 9 * c;
+        const float* fri = t.pair_friction + 5 * pk;
+        float rel[3] = {0.f, 0.f, 0.f};
+        if (HASB) {
+#pragma unroll
+          for (int q = 0; q < 3; q++) rel[q] = (float)((double)s.con_pos[3 * c + q] - s.xb[q]);
+        }
+        const double* pc = t.pairc + PUSH_PAIRC * pk;
+        const double dist = (double)s.con_dist[c];
+        const double imp = push::impedance5<true>(pc + 3, dist);
+        const float D0 = (float)fmin(1e15, imp / ((1 - imp) * pc[2]));   // 1 / max(1e-15, R0)
+        const float D1 = D0 * m.impratio;
+        const float mu = gdim > 1 ? fri[0] * rsqrtf(m.impratio) : 1.f;   // fri0 * sqrt(R1 / R0); one-row contact: plain row
+        const push::F8 qv8 = push::ld8(s.qvel);
+        float ax[9];   // body axes of the block in the world frame (columns of Rb)
+#pragma unroll
+        for (int q = 0; q < 9; q++) ax[q] = (float)s.Rb[q];
+        const int gslot = 6 * lane;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          float Jr[8];
+#pragma unroll
+          for (int d = 0; d < 8; d++) Jr[d] = 0.f;
+          float Dv = 0.f, ar = 0.f, rs = 0.f;
+          if (r < gdim) {
+            const float* frr = fr + 3 * (r < 3 ? r : r - 3);
+            const float f0 = frr[0], f1 = frr[1], f2 = frr[2];
+            if (r < 3) {
+#pragma unroll
+              for (int j = 0; j < 2; j++) Jr[j] = sr * (f0 * fi.axis[j][0] + f1 * fi.axis[j][1] + f2 * fi.axis[j][2]);
+            }
+            if (HASB) {
+#pragma unroll
+              for (int q = 0; q < 3; q++) {
+                const float ax0 = ax[q], ax1 = ax[3 + q], ax2 = ax[6 + q];  // body axis q, world frame
+                if (r < 3) {
+                  const float jp0 = ax1 * rel[2] - ax2 * rel[1], jp1 = ax2 * rel[0] - ax0 * rel[2], jp2 = ax0 * rel[1] - ax1 * rel[0];
+                  Jr[2 + q] = sbk * (q == 0 ? f0 : (q == 1 ? f1 : f2));
+                  Jr[5 + q] = sbk * (f0 * jp0 + f1 * jp1 + f2 * jp2);
+                } else {
+                  Jr[5 + q] = sbk * (f0 * ax0 + f1 * ax1 + f2 * ax2);
+                }
+              }
+            }
+            float vel = 0.f;
+#pragma unroll
+            for (int d = 0; d < 8; d++) vel += Jr[d] * qv8.v[d];
+            if (r == 0) { Dv = D0; ar = (float)(-pc[1] * (double)vel - pc[0] * imp * dist); rs = mu; }
+            else {
+              ar = (float)(-pc[1] * (double)vel);
+              Dv = r == 1 ? D1 : D1 * (fri[r - 1] * fri[r - 1]) / (fri[0] * fri[0]);
+              rs = fri[r - 1];
+            }
+          }
+          push::st8(s.J + 8 * (gslot + r), Jr);
+          s.Dr[gslot + r] = Dv; s.aref[gslot + r] = ar; s.rsc[gslot + r] = rs;
+        }
+      }
+      __syncwarp();
+
+      // ---------------------------------------------------------------- Newton solver (B.7)
+      // One loop whose body appears once in the instruction stream: [rows at the point] -> cost / forces / zones ->
+      // bookkeeping of the phase -> Newton step.  Phases: 0 cost at qacc_smooth, 1 cost at qacc_warmstart (the usual
+      // winner, evaluated last so that its rows and forces are in place), 2 back to qacc_smooth when it won, 3.. Newton.
+      int it = 0, ls_used = 0;
+      if (ngrp == 0) {
+        if (lane < 8) { s.x[lane] = s.as[lane]; s.qfc[lane] = 0.f; }
+        __syncwarp();
+      } else {
+        int zone = 0;
+        float cN = 0.f, cT = 0.f;
+        int phase = 0;
+        const float* xp = s.as;
+        float cs = 0.f, cost = 0.f, alpha = 0.f, dec = 0.f;
+        bool finishing = false;   // converged by the improvement test: stop after the next gradient (forces of the final point)
+#pragma unroll 1
+        while (true) {
+          if (phase < 3) {
+            // jar = J x - aref (row slots across lanes)
+            const push::F8 xv = push::ld8(xp);
+            for (int r = lane; r < nslot; r += 32) {
+              const push::F8 j = push::ld8(s.J + 8 * r);
+              float acc = -s.aref[r];
+#pragma unroll
+              for (int d = 0; d < 8; d++) acc += j.v[d] * xv.v[d];
+              s.jar[r] = acc;
+            }
+            __syncwarp();
+          }
+          // ---- cost of the point: Gauss term on the dof lanes, cone / half-line state of each group on its lane
+          //      (zone, forces -> s.f)
+          float cl = 0.f;
+          if (lane < 8) { const float xi = xp[lane]; cl = 0.5f * (Mi * xi - s.qs[lane]) * (xi - s.as[lane]); }
+          if (lane < ngrp) {
+            const float* pj = s.jar + 6 * lane; const float* pD = s.Dr + 6 * lane; const float* ps = s.rsc + 6 * lane;
+            float jr[6], Dv[6], rs[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) { jr[r] = pj[r]; Dv[r] = pD[r]; rs[r] = ps[r]; }
+            const float mu = rs[0];
+            int z; float n_ = 0.f, t_ = 0.f;
+            if (gdim == 1) {
+              z = jr[0] < 0 ? 1 : 0;
+            } else {
+              n_ = jr[0] * mu;
+              float tt = 0.f;
+#pragma unroll
+              for (int j = 1; j < 6; j++) { const float u = jr[j] * rs[j]; tt += u * u; }
+              t_ = sqrtf(tt);
+              if (n_ >= mu * t_ || (t_ <= 0 && n_ >= 0)) z = 0;
+              else if (mu * n_ + t_ <= 0 || (t_ <= 0 && n_ < 0)) z = 1;
+              else z = 2;
+            }
+            float fo[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) fo[r] = 0.f;
+            if (z == 1) {
+#pragma unroll
+              for (int r = 0; r < 6; r++) { cl += 0.5f * Dv[r] * jr[r] * jr[r]; fo[r] = -Dv[r] * jr[r]; }
+            } else if (z == 2) {
+              const float Dm = Dv[0] / (mu * mu * (1 + mu * mu));
+              const float NTv = n_ - mu * t_;
+              cl += 0.5f * Dm * NTv * NTv;
+              const float f0 = -Dm * NTv * mu;
+              fo[0] = f0;
+              const float f0t = -f0 / t_;
+#pragma unroll
+              for (int j = 1; j < 6; j++) fo[j] = f0t * (jr[j] * rs[j]) * rs[j];
+            }
+            float* pf = s.f + 6 * lane;
+#pragma unroll
+            for (int r = 0; r < 6; r++) pf[r] = fo[r];
+            zone = z; cN = n_; cT = t_;
+          }
+          const float c = wpe::warp_sum(cl);
+          __syncwarp();
+          if (phase == 0) { cs = c; xp = s.warm; phase = 1; continue; }
+          if (phase == 1) {
+            const bool use_warm = c <= cs;   // ties -> warm start
+            if (lane < 8) s.x[lane] = use_warm ? s.warm[lane] : s.as[lane];
+            __syncwarp();
+            xp = s.x;
+            if (!use_warm) { phase = 2; continue; }
+            cost = c; phase = 3;
+          } else if (phase == 2) {
+            cost = c; phase = 3;
+          } else {
+            const float old = cost;
+            cost = c;
+            it++;
+            const float improvement = alpha < 2.f ? alpha * (1.f - 0.5f * alpha) * dec : old - cost;
+            if (scale * improvement < m.tolerance) finishing = true;   // the next pass computes J^T f of this point and stops
+          }
+          // ---- gradient component of this lane's dof: M x - qfrc_smooth - J^T f   (row stripes: r = sub, sub + 4, ...)
+          float qf = 0.f;
+#pragma unroll 2
+          for (int r = sub; r < nslot; r += 4) qf += s.J[8 * r + li] * s.f[r];
+          qf += __shfl_xor_sync(FULL, qf, 8);
+          qf += __shfl_xor_sync(FULL, qf, 16);
+          const float xi = s.x[li];
+          const float grad = (li < NV) ? Mi * xi - s.qs[li] - qf : 0.f;
+          float gn = grad * grad;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) gn += __shfl_xor_sync(FULL, gn, o);
+          gn = sqrtf(gn);
+          if (finishing || (it > 0 && scale * gn < m.tolerance) || it >= m.iterations) {
+            if (lane < 8) s.qfc[lane] = qf;
+            break;
+          }
+          // ---- Hessian J^T (cone Hessians) J as a sum of weighted outer products of Jacobian rows (see hsrb_push.cuh):
+          //      quadratic-zone group: sum_r D_r J_r J_r^T;  cone-zone contact: Dm (p p^T + k q q^T) - Dm k sum_{a>=1} s_a^2 J_a J_a^T
+          if (lane < ngrp) {
+            const float* pD = s.Dr + 6 * lane; const float* ps = s.rsc + 6 * lane;
+            float wr_[6], wp = 0.f, wq = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; r++) wr_[r] = zone == 1 ? pD[r] : 0.f;
+            if (zone == 2) {
+              const float mu = ps[0];
+              const float Dm = pD[0] / (mu * mu * (1 + mu * mu)), NTv = cN - mu * cT, invT = 1.0f / cT;
+              const float kap = mu * NTv * invT;
+              const float* pj = s.jar + 6 * lane;
+              float pvv[8], qv[8];
+              {
+                const push::F8 j = push::ld8(s.J + 8 * (6 * lane));
+#pragma unroll
+                for (int d = 0; d < 8; d++) { pvv[d] = mu * j.v[d]; qv[d] = 0.f; }
+              }
+#pragma unroll
+              for (int aa = 1; aa < 6; aa++) {
+                const float sa = ps[aa];
+                const float cq = pj[aa] * sa * invT * sa, cp = -mu * cq;
+                const push::F8 j = push::ld8(s.J + 8 * (6 * lane + aa));
+#pragma unroll
+                for (int d = 0; d < 8; d++) { pvv[d] += cp * j.v[d]; qv[d] += cq * j.v[d]; }
+                wr_[aa] = -Dm * kap * sa * sa;
+              }
+              wp = Dm; wq = Dm * kap;
+              push::st8(s.PQ + 16 * lane, pvv); push::st8(s.PQ + 16 * lane + 8, qv);
+            }
+            float* pw = s.wrow + 6 * lane;
+#pragma unroll
+            for (int r = 0; r < 6; r++) pw[r] = wr_[r];
+            s.wpq[2 * lane] = wp; s.wpq[2 * lane + 1] = wq;
+          }
+          __syncwarp();
+          float Hr[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) Hr[j] = 0.f;
+#pragma unroll 2
+          for (int r = sub; r < nslot; r += 4) {
+            const float ji = s.J[8 * r + li] * s.wrow[r];
+            const push::F8 jv_ = push::ld8(s.J + 8 * r);
+#pragma unroll
+            for (int j = 0; j < 8; j++) Hr[j] += ji * jv_.v[j];
+          }
+          for (int c = sub; c < ngrp; c += 4) {
+            const float wpc = s.wpq[2 * c];
+            if (wpc != 0.f) {
+              const float pi_ = s.PQ[16 * c + li] * wpc, qi_ = s.PQ[16 * c + 8 + li] * s.wpq[2 * c + 1];
+              const push::F8 pv_ = push::ld8(s.PQ + 16 * c), qv_ = push::ld8(s.PQ + 16 * c + 8);
+#pragma unroll
+              for (int j = 0; j < 8; j++) Hr[j] += pi_ * pv_.v[j] + qi_ * qv_.v[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            Hr[j] += __shfl_xor_sync(FULL, Hr[j], 8);
+            Hr[j] += __shfl_xor_sync(FULL, Hr[j], 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) if (li == j) Hr[j] += Mi;
+          // ---- Cholesky H = L L^T: lane i holds row i; column k is finished by a broadcast of the pivot and one
+          //      shuffle per trailing column (the four 8-lane segments of the warp work redundantly)
+          float inv_diag = 1.f;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            float dkk = __shfl_sync(FULL, Hr[k], k, 8);
+            if (!(dkk > 1e-15f)) { dkk = 1e-15f; flags |= FLAG_CHOL; }
+            const float inv = rsqrtf(dkk);
+            const float lkk = dkk * inv;
+            const float lik = (li == k) ? lkk : Hr[k] * inv;   // L[i][k] for i >= k
+            Hr[k] = lik;
+            if (li == k) inv_diag = inv;
+#pragma unroll
+            for (int j = k + 1; j < 8; j++) {
+              const float ljk = __shfl_sync(FULL, lik, j, 8);
+              Hr[j] -= lik * ljk;                               // meaningful for i >= j
+            }
+          }
+          // ---- forward solve L y = -grad
+          float acc = -grad, y = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const float yk = __shfl_sync(FULL, acc * inv_diag, k, 8);
+            if (li == k) y = yk;
+            acc -= Hr[k] * yk;                                  // meaningful for i > k
+          }
+          // ---- backward solve L^T s = y: column k of L gathered through shared memory
+          __syncwarp();
+          if (sub == 0) push::st8(s.L + 8 * li, Hr);
+          __syncwarp();
+          acc = y;
+          float sv = 0.f;
+#pragma unroll
+          for (int k = 7; k >= 0; k--) {
+            const float xk = __shfl_sync(FULL, acc * inv_diag, k, 8);
+            if (li == k) sv = xk;
+            acc -= s.L[8 * k + li] * xk;                        // L[k][li], meaningful for li < k
+          }
+          if (li >= NV) sv = 0.f;
+          if (sub == 0) s.srch[li] = sv;
+          float sn = sv * sv, q1 = sv * (Mi * xi - s.qs[li]), q2 = 0.5f * sv * (Mi * sv);
+          dec = -grad * sv;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            dec += __shfl_xor_sync(FULL, dec, o); sn += __shfl_xor_sync(FULL, sn, o);
+            q1 += __shfl_xor_sync(FULL, q1, o); q2 += __shfl_xor_sync(FULL, q2, o);
+          }
+          sn = sqrtf(sn);
+          __syncwarp();
+          if (!(sn >= 1e-15f)) {
+            if (lane < 8) s.qfc[lane] = qf;
+            break;
+          }
+          // ---- jv = J search (row slots across lanes)
+          {
+            const push::F8 sv8 = push::ld8(s.srch);
+            for (int r = lane; r < nslot; r += 32) {
+              const push::F8 j = push::ld8(s.J + 8 * r);
+              float accv = 0.f;
+#pragma unroll
+              for (int d = 0; d < 8; d++) accv += j.v[d] * sv8.v[d];
+              s.jv[r] = accv;
+            }
+          }
+          __syncwarp();
+          const float gtol = m.tolerance * m.ls_tolerance * sn / scale;
+          // ---- exact line search: root of the 1-D derivative (safeguarded Newton with bracketing); the group lanes hold
+          //      the coefficients of their group's cost along the search direction
+          float l0 = 0.f, l1c = 0.f, l2c = 0.f, l3 = 0.f, l4 = 0.f, l6 = 0.f, l7 = 0.f, l9 = 0.f, mu_ = 1.f;
+          if (lane < ngrp) {
+            const float* pj = s.jar + 6 * lane; const float* pvv = s.jv + 6 * lane; const float* pD = s.Dr + 6 * lane;
+            const float* ps = s.rsc + 6 * lane;
+            float uu = 0.f, uv = 0.f, vv = 0.f, Q1 = 0.f, Q2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+              const float xx = pj[r], v = pvv[r], Dv = pD[r];
+              Q1 += Dv * xx * v; Q2 += 0.5f * Dv * v * v;
+              if (r > 0) { const float u = xx * ps[r], sv2 = v * ps[r]; uu += u * u; uv += u * sv2; vv += sv2 * sv2; }
+            }
+            mu_ = ps[0];
+            l0 = pj[0] * mu_; l1c = pvv[0] * mu_;
+            l9 = gdim == 1 ? -1.f : pD[0] / (mu_ * mu_ * (1 + mu_ * mu_));
+            l2c = uu; l3 = uv; l4 = vv; l6 = Q1; l7 = Q2;
+          }
+          {
+            // At alpha = 0 the derivative along the Newton direction is grad . s = -dec and its slope s^T H s = dec (H s = -grad):
+            // no evaluation needed; the first trial point is the full Newton step.
+            float d1 = -dec, d2 = dec, nxt = 0.f;
+            int nev = 1;
+            float lo = 0.f, hi = -1.f, dlo = d1, dhi = 0.f;
+            const float rel = 3.4526698e-4f;  // sqrt(FLT_EPSILON)
+            bool conv = fabsf(d1) < gtol, tiny = false;
+            alpha = 0.f;
+#pragma unroll 1
+            while (!conv && nev <= m.ls_iterations) {
+              const float step = d2 > 1e-15f ? -d1 / d2 : (d1 < 0 ? 1.f : -1.f);
+              nxt = alpha + step;
+              if (hi >= 0 && !(lo < nxt && nxt < hi)) nxt = 0.5f * (lo + hi);
+              if (nxt <= 0 && hi < 0) nxt = alpha * 0.5f;
+              if (nxt == alpha) break;
+              tiny = fabsf(nxt - alpha) <= rel * fabsf(nxt);
+              // derivative of the cost along the search direction and its slope at nxt
+              {
+                const float N = l0 + nxt * l1c;
+                const float tsq = l2c + nxt * (2 * l3 + nxt * l4);
+                const float rT = tsq > 0 ? rsqrtf(tsq) : 0.f;     // 1 / T (used in the cone zone only, where T > 0)
+                const float Tn = tsq * rT;
+                const bool quad = l9 < 0;                          // one-row group: half-line instead of a cone
+                const bool top = quad ? !(N < 0) : ((N >= mu_ * Tn) || (Tn <= 0 && N >= 0));
+                const bool bottom = quad ? (N < 0) : ((mu_ * N + Tn <= 0) || (Tn <= 0 && N < 0));
+                const float NTv = N - mu_ * Tn;
+                const float T1 = (l3 + nxt * l4) * rT;
+                const float T2 = (l4 - T1 * T1) * rT;
+                const float tt = l1c - mu_ * T1;
+                const float lm1 = l9 * NTv * tt, lm2 = l9 * (tt * tt - NTv * mu_ * T2);
+                const float lb1 = l6 + 2 * nxt * l7, lb2 = 2 * l7;
+                float e1 = top ? 0.f : (bottom ? lb1 : lm1), e2 = top ? 0.f : (bottom ? lb2 : lm2);
+                if (lane >= ngrp) { e1 = 0.f; e2 = 0.f; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { e1 += __shfl_xor_sync(FULL, e1, o); e2 += __shfl_xor_sync(FULL, e2, o); }
+                d1 = e1 + q1 + 2 * nxt * q2;
+                d2 = e2 + 2 * q2;
+              }
+              alpha = nxt;
+              if (d1 < 0) { if (alpha > lo) { lo = alpha; dlo = d1; } }
+              else if (hi < 0 || alpha < hi) { hi = alpha; dhi = d1; }
+              conv = fabsf(d1) < gtol || tiny;
+              nev++;
+            }
+            ls_used += nev;
+            if (!conv) {
+              if (hi >= 0 && (lo <= 0 || fabsf(dhi) < fabsf(dlo))) alpha = (lo > 0 || fabsf(dhi) < fabsf(dlo)) ? hi : 0.f;
+              else alpha = lo;
+            }
+          }
+          if (alpha == 0.f) {
+            if (lane < 8) s.qfc[lane] = qf;
+            break;
+          }
+          if (lane < 8) s.x[lane] += alpha * s.srch[lane];
+          for (int r = lane; r < nslot; r += 32) s.jar[r] += alpha * s.jv[r];
+          __syncwarp();
+        }
+        __syncwarp();
+      }
+      n_iter += it; n_ls += ls_used;
+      kflop += algorithmic_flops(m, false, ncon, nefc, it, ls_used, npflop);   // slides + free box: M is constant
+
+      // ---------------------------------------------------------------- goal test on the poses of this forward pass
+      bool reached = false;
+      if (HASB && a.cfg.has_goal) {
+        const double dx = s.xb[0] - (double)s.mocap[0], dy = s.xb[1] - (double)s.mocap[1], dz = s.xb[2] - (double)s.mocap[2];
+        reached = sqrt(dx * dx + dy * dy + dz * dz) < (double)a.cfg.geofence;
+      }
+      // ---------------------------------------------------------------- Euler with implicit joint damping (B.8)
+      bool bad = false;
+      if (lane < NV) {
+        const float xi = s.x[lane];
+        const float ai = m.any_damping ? (s.qs[lane] + s.qfc[lane]) / (Mi + dt * dampi) : xi;
+        s.warm[lane] = xi;
+        const float v = s.qvel[lane] + dt * ai;
+        s.qvel[lane] = v;
+        if (!(fabsf(v) < 1e6f)) bad = true;
+        if (lane < 5) s.qpos[lane] += dt * v;
+      }
+      if (__any_sync(FULL, bad)) flags |= FLAG_BAD_NUM;
+      __syncwarp();
+      if (HASB) {
+        const float om0 = s.qvel[5], om1 = s.qvel[6], om2 = s.qvel[7];
+        const float ang = sqrtf(om0 * om0 + om1 * om1 + om2 * om2);
+        float qq[4] = {s.qpos[5], s.qpos[6], s.qpos[7], s.qpos[8]};
+        quatnormalize(qq);
+        if (ang * dt > 1e-15f) {
+          // rotation by ang * dt about omega: dq = [cos h, sin(h) / ang * omega], h = ang dt / 2 (series below h = 0.5 rad)
+          const float hh = 0.5f * ang * dt;
+          float ch, sn_;
+          if (hh < 0.5f) {
+            const float h2 = hh * hh;
+            ch = 1.f + h2 * (-0.5f + h2 * (4.1666667e-2f + h2 * (-1.3888889e-3f + h2 * (2.4801587e-5f - h2 * 2.7557319e-7f))));
+            sn_ = 0.5f * dt * (1.f + h2 * (-1.6666667e-1f + h2 * (8.3333333e-3f + h2 * (-1.9841270e-4f + h2 * 2.7557319e-6f))));
+          } else {
+            ch = cosf(hh); sn_ = sinf(hh) / ang;
+          }
+          float dq[4] = {ch, sn_ * om0, sn_ * om1, sn_ * om2};
+          quatmul(qq, dq, qq);
+        }
+        quatnormalize(qq);
+        __syncwarp();
+        if (lane < 4) s.qpos[5 + lane] = qq[lane];
+        __syncwarp();
+      }
+      taken++;
+      if (reached) { success = true; break; }
+    }
+    // ------------------------------------------------------------------ results: HBM once per action
+    {
+      __syncwarp();
+      float* st = a.state + (size_t)env * a.S;
+      const int nobs = nq + NV;
+      for (int i = lane; i < nq + 2 * NV; i += 32) {
+        const float v = i < nq ? s.qpos[i] : (i < nq + NV ? s.qvel[i - nq] : s.warm[i - nq - NV]);
+        st[i] = v;
+        if (a.obs && i < nobs) a.obs[(size_t)env * nobs + i] = v;
+      }
+      if (lane == 0) {
+        if (a.reward) a.reward[env] = success ? 1.0f : 0.0f;
+        if (a.done) a.done[env] = success ? 1 : 0;
+        if (a.success) a.success[env] = success ? 1 : 0;
+        if (a.taken) a.taken[env] = taken;
+        if (a.bad) a.bad[env] = (unsigned char)flags;
+        atomicAdd(a.stats + ST_SUBSTEPS, (unsigned long long)taken);
+        atomicAdd(a.stats + ST_ITERS, (unsigned long long)n_iter);
+        atomicAdd(a.stats + ST_NARROW, (unsigned long long)narrow_tot);
+        atomicAdd(a.stats + ST_LSEVAL, (unsigned long long)n_ls);
+        atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)sumcon);
+        atomicAdd(a.stats + ST_ROWS, (unsigned long long)sumefc);
+        atomicAdd(a.stats + ST_FLOPS, (unsigned long long)kflop);
+        if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
+      }
+      __syncwarp();
+    }
+  }
+}
+#endif  // HSRB_WPE_IMPL

@@ -114,7 +114,7 @@ class BatchedHSREnv:
         if lanes_per_env:
             _lib.check(self._lib.hsrb_config(self._h, int(lanes_per_env), 0, 0))
         # "auto": fast kernel (hsrb_push.cuh) for the sliding-base + <=1 block family, else the general kernel
-        self.kernel_path = _lib.check(self._lib.hsrb_set_path(self._h, {"auto": 0, "general": 1, "fast": 2}[kernel]))
+        self.kernel_path = _lib.check(self._lib.hsrb_set_path(self._h, {"auto": 0, "general": 1, "fast": 2, "lockstep": 2, "wpe": 3}[kernel]))
         m = self.model
         self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
         self.state_dim = self.nq + self.nv   # what the kernel writes: qpos | qvel
@@ -413,7 +413,7 @@ class BatchedHSREnv:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.hsrb_launch_info(self._h, v))
         return dict(lanes_per_env=v[0], smem_per_env=v[1], envs_per_sm=v[2], grid=v[3],
-                    kernel={1: "general", 2: "fast"}.get(v[4], "?"), threads_per_block=v[5])
+                    kernel={1: "general", 2: "fast", 3: "wpe"}.get(v[4], "?"), threads_per_block=v[5])
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

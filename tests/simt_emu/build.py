@@ -10,7 +10,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 LIB = ROOT / "oracle" / "_build" / "libpush_emu.so"
-DEPS = [HERE / "emu_push.cpp", HERE / "simt_emu.h", ROOT / "hsr_env_b200/csrc/hsrb_push.cuh", ROOT / "hsr_env_b200/csrc/hsr_core.h",
+DEPS = [HERE / "emu_push.cpp", HERE / "simt_emu.h", ROOT / "hsr_env_b200/csrc/hsrb_push.cuh", ROOT / "hsr_env_b200/csrc/hsrb_wpe.cuh", ROOT / "hsr_env_b200/csrc/hsr_core.h",
         ROOT / "hsr_env_b200/csrc/hsrb_kernels.cuh", ROOT / "hsr_env_b200/csrc/hsr_model.h"]
 
 

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 CASES = [("c1_readme", 64, False, "general"), ("c2_push", 256, False, "general"), ("c1b_readme_block", 64, False, "general"),
          ("c5_clutter", 64, False, "general"), ("c3_arm", 64, True, "general"), ("f2_cupboard", 64, True, "general"),
-         ("c1_readme", 64, False, "fast"), ("c2_push", 256, False, "fast"), ("c1b_readme_block", 64, False, "fast")]
+         ("c1_readme", 64, False, "fast"), ("c2_push", 256, False, "fast"), ("c1b_readme_block", 64, False, "fast"),
+         ("c1_readme", 64, False, "wpe"), ("c2_push", 256, False, "wpe"), ("c1b_readme_block", 64, False, "wpe")]
 
 
 def make_env(name, n, **kw):
@@ -98,7 +99,7 @@ def test_reset_streams_bit_exact(models, ports):
     env.close()
 
 
-@pytest.mark.parametrize("kernel", ["general", "fast"])
+@pytest.mark.parametrize("kernel", ["general", "fast", "wpe"])
 def test_success_flags_bit_exact_and_early_exit(kernel, models, ports):
     """Given matched states, done/reward/substeps_taken equal the oracle's (strict < geofence, freeze at success)."""
     from hsr_env_b200.env import BatchedHSREnv
@@ -156,7 +157,8 @@ def test_env_result_independent_of_batch_and_lanes(models):
     act = torch.rand(512, 2, generator=gen) * 2 - 1
     outs = []
     cases = ((512, 0, 0, "general"), (512, 0, 4, "general"), (512, 0, 32, "general"), (256, 256, 0, "general"),
-             (512, 0, 0, "fast"), (256, 256, 0, "fast"), (96, 416, 0, "fast"))
+             (512, 0, 0, "fast"), (256, 256, 0, "fast"), (96, 416, 0, "fast"),
+             (512, 0, 0, "wpe"), (256, 256, 0, "wpe"), (96, 416, 0, "wpe"))
     for n, off, lanes, kernel in cases:
         env = BatchedHSREnv("c2_push.hsrb", goals, n_envs=n, device="cuda:0", seed=5, env_id_offset=off,
                             lanes_per_env=lanes, kernel=kernel)
@@ -167,13 +169,15 @@ def test_env_result_independent_of_batch_and_lanes(models):
     base = outs[0]
     # lane layouts / kernels change the order of reductions: agreement to rounding (40 substeps of contact dynamics
     # amplify it), not bit-exact; a handful of environments may sit on a contact-activation boundary
-    for other in (outs[1], outs[2], outs[4]):
+    for other in (outs[1], outs[2], outs[4], outs[7]):
         bad = np.abs(other - base).max(axis=1) > 2e-3
         assert bad.mean() <= 0.02, bad.mean()
     # same kernel and layout, different shard (rank) of the global env ids: bit-exact
     assert np.array_equal(outs[3], base[256:])
     assert np.array_equal(outs[5], outs[4][256:])
     assert np.array_equal(outs[6], outs[4][416:])
+    assert np.array_equal(outs[8], outs[7][256:])
+    assert np.array_equal(outs[9], outs[7][416:])
 
 
 def test_fast_kernel_matches_general_kernel_along_rollouts():

@@ -24,7 +24,9 @@ def emu():
 
 
 @pytest.mark.parametrize("name,n,G", [("c2_push", 96, 8), ("c2_push", 48, 16), ("c2_push", 32, 32),
-                                       ("c1b_readme_block", 32, 8), ("c1_readme", 32, 8)])
+                                       ("c1b_readme_block", 32, 8), ("c1_readme", 32, 8),
+                                       # G = 1: the warp-per-environment kernel (hsrb_wpe.cuh)
+                                       ("c2_push", 96, 1), ("c1b_readme_block", 32, 1), ("c1_readme", 32, 1)])
 def test_emulated_kernel_matches_oracle(name, n, G, models, ports, emu):
     model, port = models[name], ports[name]
     qpos, qvel, warm, ctrl = rollout_states(port, model, n, seed=len(name) * 7, float32=True)
@@ -36,7 +38,8 @@ def test_emulated_kernel_matches_oracle(name, n, G, models, ports, emu):
     assert np.mean(ev > TOL) <= 0.02, np.sort(ev)[-5:]
 
 
-def test_emulated_kernel_limits_and_hull_contacts(models, ports, emu):
+@pytest.mark.parametrize("G", [8, 1])
+def test_emulated_kernel_limits_and_hull_contacts(G, models, ports, emu):
     """No-block model: joint-limit rows and robot-hull / pan contacts (states the roll-outs above do not reach)."""
     model, port = models["c1_readme"], ports["c1_readme"]
     rng = np.random.default_rng(0)
@@ -48,7 +51,7 @@ def test_emulated_kernel_limits_and_hull_contacts(models, ports, emu):
     qpos, qvel, warm, ctrl = [x.astype(np.float32).astype(np.float64) for x in (qpos, qvel, warm, ctrl)]
     seen_rows = 0
     for _ in range(3):
-        out = emu.step(model, qpos, qvel, warm, ctrl, nsub=1, G=8)
+        out = emu.step(model, qpos, qvel, warm, ctrl, nsub=1, G=G)
         ref = port.step(qpos, qvel, warm, ctrl, nsub=1)
         assert rel_err(out["qpos"], ref["qpos"]).max() <= TOL
         assert rel_err(out["qvel"], ref["qvel"]).max() <= TOL
@@ -57,7 +60,8 @@ def test_emulated_kernel_limits_and_hull_contacts(models, ports, emu):
     assert seen_rows > 100
 
 
-def test_emulated_kernel_goal_flags_and_early_exit(models, ports, emu):
+@pytest.mark.parametrize("G", [8, 1])
+def test_emulated_kernel_goal_flags_and_early_exit(G, models, ports, emu):
     """Per-substep goal test with early break: flags and executed-substep counts equal the fp32 port's."""
     model, port = models["c2_push"], ports["c2_push"]
     n = 32
@@ -70,7 +74,7 @@ def test_emulated_kernel_goal_flags_and_early_exit(models, ports, emu):
         ref = port.step(qpos, qvel, warm, ctrl, mocap, nsub=20, use_float=True)
     finally:
         port.set_goals(None)
-    out = emu.step(model, qpos, qvel, warm, ctrl, mocap, nsub=20, G=8, geofence=.05)
+    out = emu.step(model, qpos, qvel, warm, ctrl, mocap, nsub=20, G=G, geofence=.05)
     assert 0.05 < out["success"].mean() < 0.95
     same = out["success"] == ref["success"]
     assert same.mean() >= 0.9
@@ -78,14 +82,15 @@ def test_emulated_kernel_goal_flags_and_early_exit(models, ports, emu):
     assert np.all(out["taken"][out["success"] == 0] == 20)
 
 
-def test_emulated_kernel_separating_direction_cache(models, ports, emu, monkeypatch):
+@pytest.mark.parametrize("G", [8, 1])
+def test_emulated_kernel_separating_direction_cache(G, models, ports, emu, monkeypatch):
     """The cached separating direction of a candidate pair (mpr_penetration's `sep`) only shortens queries that end
     without a contact: a 40-substep action gives the same trajectory with the cache switched off (HSRB_OPTS bit 0)."""
     model, port = models["c2_push"], ports["c2_push"]
     qpos, qvel, warm, ctrl = rollout_states(port, model, 32, seed=5, float32=True)
-    out = emu.step(model, qpos, qvel, warm, ctrl, nsub=40, G=8, threads=64)
+    out = emu.step(model, qpos, qvel, warm, ctrl, nsub=40, G=G, threads=64)
     monkeypatch.setenv("HSRB_OPTS", "1")
-    ref = emu.step(model, qpos, qvel, warm, ctrl, nsub=40, G=8, threads=64)
+    ref = emu.step(model, qpos, qvel, warm, ctrl, nsub=40, G=G, threads=64)
     assert np.all(out["flags"] == 0) and np.all(ref["flags"] == 0)
     assert int(ref["stats"][2]) == int(out["stats"][2]) > 40 * 32          # same narrowphase calls, some convex-convex
     same = np.all(out["qpos"] == ref["qpos"], axis=1) & np.all(out["qvel"] == ref["qvel"], axis=1)
