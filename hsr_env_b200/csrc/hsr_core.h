@@ -33,6 +33,10 @@
 #define HSR_HDN inline
 #endif
 
+#if defined(HSR_SCAN_NOISE) && !defined(__CUDA_ARCH__)
+static thread_local unsigned long long hsr_scan_noise_seed = 0;   // 0 = off
+#endif
+
 namespace hsr {
 
 // Geometry precision.  Body / geom poses, the narrowphase and the goal distance are evaluated in double whatever
@@ -83,6 +87,8 @@ struct HostGrp {
   template <typename T> HSR_HD T sum(T x) const { return x; }
   template <typename T> HSR_HD void argmax(T&, int&) const {}
   HSR_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  HSR_HD double max(double x) const { return x; }
+  HSR_HD int min(int x) const { return x; }
   HSR_HD void sync() const {}
 };
 
@@ -136,6 +142,16 @@ struct DevGrp {
   __device__ __forceinline__ unsigned ballot(bool p) const {
     unsigned b = __ballot_sync(mask, p) >> shift;
     return (G_ == 32) ? b : (b & ((1u << G_) - 1u));
+  }
+  __device__ __forceinline__ double max(double x) const {
+#pragma unroll
+    for (int o = G_ / 2; o > 0; o >>= 1) { const double t = __shfl_xor_sync(mask, x, o); x = t > x ? t : x; }
+    return x;
+  }
+  __device__ __forceinline__ int min(int x) const {
+#pragma unroll
+    for (int o = G_ / 2; o > 0; o >>= 1) { const int t = __shfl_xor_sync(mask, x, o); x = t < x ? t : x; }
+    return x;
   }
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
@@ -621,59 +637,120 @@ template <typename T> HSR_HD T origin_tri_dist2(V3<T> a, V3<T> b, V3<T> c, V3<T>
 // compare triple products of vectors that shrink with the penetration depth against libccd's DBL_EPSILON-scale
 // thresholds, which fp32 cannot resolve (a 0.1 mm contact came out with a different face normal).  Only the
 // vertex scan of a hull (the bulk of the work) runs in T; its result is an index, i.e. exact.
-#if defined(__CUDACC__)
-// argmax_i <v_i, l> over a hull stored as float4, lanes of the group striding over the vertices, two vertices per
-// iteration; ties go to the lowest index (as the scalar scan below)
-#ifndef HSR_HULLSCAN_ATTR
-#define HSR_HULLSCAN_ATTR __forceinline__   // measured: +0.8 % over an out-of-line scan once the portal refinement is inlined
+// Support ties (oracle/mjstep.py support()): a local direction component within SUPPORT_TIE of zero counts as positive,
+// and among the hull vertices whose support is within SUPPORT_TIE of the maximum the lowest index wins.  Face-aligned
+// directions are structural in this path (the portal refinement converges to face normals, resting contacts line up
+// with box axes); with plain comparisons the winner is rounding noise and differs between implementations (fp64 numpy,
+// fp64 g++, CUDA with FMA contraction), moving the contact point across the face.
+#define HSR_SUPPORT_TIE 1e-12
+// the vertex scan runs in T; vertices within this distance of the scanned maximum are re-evaluated in double
+template <typename T> HSR_HD T scan_slack(T best) { return sizeof(T) == 4 ? T(1e-6) * (T(1) + fabs(best)) : T(HSR_SUPPORT_TIE); }
+// <v, l> in double, evaluated left to right without contraction (the same number on every implementation)
+HSR_HD double dot3_exact(double x, double y, double z, double lx, double ly, double lz) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(__dadd_rn(__dmul_rn(x, lx), __dmul_rn(y, ly)), __dmul_rn(z, lz));
+#else
+  volatile double a = x * lx, b = y * ly, c = z * lz;
+  volatile double ab = a + b;
+  return ab + c;
 #endif
-template <typename Grp>
-__device__ HSR_HULLSCAN_ATTR int hull_scan4(const float4* __restrict__ v, int n, float lx, float ly, float lz, const Grp& g) {
-  float best = -FLT_MAX;
-  int bi = 0x7fffffff;
-  int i = g.lane;
-#pragma unroll 2
-  for (; i + Grp::G < n; i += 2 * Grp::G) {
-    const float4 a = v[i], b = v[i + Grp::G];
-    const float va = a.x * lx + a.y * ly + a.z * lz, vb = b.x * lx + b.y * ly + b.z * lz;
-    if (va > best) { best = va; bi = i; }
-    if (vb > best) { best = vb; bi = i + Grp::G; }
-  }
-  if (i < n) {
-    const float4 a = v[i];
-    const float va = a.x * lx + a.y * ly + a.z * lz;
-    if (va > best) { best = va; bi = i; }
-  }
-  g.argmax(best, bi);
-  return bi;
+}
+
+// argmax_i <v_i, l> over the n vertices of a hull (stride `st` floats / Ts per vertex), lanes of the group striding over
+// the vertices: scan in T tracking each lane's best and second-best value; when exactly one vertex of the whole group is
+// within the slack of the scanned maximum (the usual case) that vertex wins; otherwise the candidates are re-evaluated
+// in double and the lowest index within HSR_SUPPORT_TIE of the maximum wins.
+template <typename T> HSR_HD void load_vert(const T* p, int st, T& x, T& y, T& z) { (void)st; x = p[0]; y = p[1]; z = p[2]; }
+#if defined(__CUDACC__)
+template <> HSR_HD void load_vert<float>(const float* p, int st, float& x, float& y, float& z) {
+  if (st == 4) { const float4 a = *reinterpret_cast<const float4*>(p); x = a.x; y = a.y; z = a.z; }   // 16-byte vertices: one 128-bit load
+  else { x = p[0]; y = p[1]; z = p[2]; }
 }
 #endif
+template <typename T, typename Grp>
+HSR_HD int hull_argmax(const T* __restrict__ v, int st, int n, V3<double> dl, const Grp& g) {
+  const T lx = (T)dl.x, ly = (T)dl.y, lz = (T)dl.z;
+  T best = -FLT_MAX, second = -FLT_MAX;
+  int bi = 0x7fffffff;
+  for (int i = g.lane; i < n; i += Grp::G) {
+    T px, py, pz;
+    load_vert(v + (size_t)st * i, st, px, py, pz);
+    T val = px * lx + py * ly + pz * lz;
+#if defined(HSR_SCAN_NOISE) && !defined(__CUDA_ARCH__)
+    // ORACLE-SIDE ONLY (oracle/cpu_port.cpp): relative noise of the size of an fp32 rounding error on the scanned
+    // support values, to find the states whose result depends on how a near-tie between hull vertices is rounded
+    // (tests/golden/make_golden.py `sensitive`)
+    if (hsr_scan_noise_seed) {
+      hsr_scan_noise_seed = hsr_scan_noise_seed * 6364136223846793005ull + 1442695040888963407ull;
+      val += (T)(fabs((double)val) * 2.4e-7 * ((double)(hsr_scan_noise_seed >> 40) / 16777216.0 - 0.5));
+    }
+#endif
+    if (val > best) bi = i;
+    second = fmax(second, fmin(best, val));
+    best = fmax(best, val);
+  }
+  T gbest = best;
+  int gbi = bi;
+  g.argmax(gbest, gbi);
+  const T cut = gbest - scan_slack(gbest);
+  const unsigned involved = g.ballot(best >= cut);            // lanes holding a candidate
+  const unsigned multi = g.ballot(second >= cut);             // lanes holding more than one
+  if (multi == 0 && (involved & (involved - 1)) == 0) return gbi;
+  if (multi == 0) {
+    // tie between vertices of different lanes, one candidate per lane (the usual tie: a face of the hull): the lanes'
+    // best vertices in double, lowest index within HSR_SUPPORT_TIE of the maximum
+    double dv = -DBL_MAX;
+    if (best >= cut) {
+      T px, py, pz;
+      load_vert(v + (size_t)st * bi, st, px, py, pz);
+      dv = dot3_exact((double)px, (double)py, (double)pz, dl.x, dl.y, dl.z);
+    }
+    const double dmax = g.max(dv);
+    return g.min(dv >= dmax - HSR_SUPPORT_TIE ? bi : 0x7fffffff);
+  }
+  // some lane holds several candidates: re-scan, candidates in double
+  double dbest = -DBL_MAX;
+  if (best >= cut) {
+    for (int i = g.lane; i < n; i += Grp::G) {
+      T px, py, pz;
+      load_vert(v + (size_t)st * i, st, px, py, pz);
+      const T val = px * lx + py * ly + pz * lz;
+      if (val >= cut) { const double d = dot3_exact((double)px, (double)py, (double)pz, dl.x, dl.y, dl.z); if (d > dbest) dbest = d; }
+    }
+  }
+  dbest = g.max(dbest);
+  int mi = 0x7fffffff;
+  if (best >= cut) {
+    for (int i = g.lane; i < n; i += Grp::G) {
+      T px, py, pz;
+      load_vert(v + (size_t)st * i, st, px, py, pz);
+      const T val = px * lx + py * ly + pz * lz;
+      if (val >= cut && i < mi && dot3_exact((double)px, (double)py, (double)pz, dl.x, dl.y, dl.z) >= dbest - HSR_SUPPORT_TIE) mi = i;
+    }
+  }
+  return g.min(mi);
+}
 
 template <typename T, typename Grp>
 HSR_HD V3<double> support_d(const Geom<T>& ge, V3<double> d, const Grp& g) {
   typedef double W;
   const W* R = ge.mat;
   V3<W> dl = multv(R, d), res;
+  const W tie = -HSR_SUPPORT_TIE;
   if (ge.type == GEOM_BOX) {
-    res = mk<W>(dl.x >= 0 ? (W)ge.size[0] : -(W)ge.size[0], dl.y >= 0 ? (W)ge.size[1] : -(W)ge.size[1],
-                dl.z >= 0 ? (W)ge.size[2] : -(W)ge.size[2]);
+    res = mk<W>(dl.x >= tie ? (W)ge.size[0] : -(W)ge.size[0], dl.y >= tie ? (W)ge.size[1] : -(W)ge.size[1],
+                dl.z >= tie ? (W)ge.size[2] : -(W)ge.size[2]);
   } else if (ge.type == GEOM_CYLINDER) {
     W n = sqrt(dl.x * dl.x + dl.y * dl.y);
-    res = mk<W>(0, 0, dl.z >= 0 ? (W)ge.size[1] : -(W)ge.size[1]);
+    res = mk<W>(0, 0, dl.z >= tie ? (W)ge.size[1] : -(W)ge.size[1]);
     if (n > 1e-15) { res.x = dl.x / n * (W)ge.size[0]; res.y = dl.y / n * (W)ge.size[0]; }
 #if defined(__CUDACC__)
   } else if (ge.verts4) {
-    const int bi = hull_scan4(reinterpret_cast<const float4*>(ge.verts4), ge.nvert, (float)dl.x, (float)dl.y, (float)dl.z, g);
+    const int bi = hull_argmax<float>(ge.verts4, 4, ge.nvert, dl, g);
     res = mk<W>((W)ge.verts4[4 * bi], (W)ge.verts4[4 * bi + 1], (W)ge.verts4[4 * bi + 2]);
 #endif
   } else {
-    T lx = (T)dl.x, ly = (T)dl.y, lz = (T)dl.z;
-    T best = -FLT_MAX; int bi = 0x7fffffff;
-    for (int i = g.lane; i < ge.nvert; i += Grp::G) {
-      T v = ge.verts[3 * i] * lx + ge.verts[3 * i + 1] * ly + ge.verts[3 * i + 2] * lz;
-      if (v > best) { best = v; bi = i; }
-    }
-    g.argmax(best, bi);
+    const int bi = hull_argmax<T>(ge.verts, 3, ge.nvert, dl, g);
     res = mk<W>((W)ge.verts[3 * bi], (W)ge.verts[3 * bi + 1], (W)ge.verts[3 * bi + 2]);
   }
   return ge.pos + mulv(R, res);

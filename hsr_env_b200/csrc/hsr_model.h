@@ -180,6 +180,9 @@ struct HostModel {
     }
     // default capacities: 4 plane contacts per block, up to 8 box-box per block pair / block-pan, a few hull contacts
     m.ncon_max = 8 + 4 * m.nblock + (m.nblock > 1 ? 4 * m.nblock : 0);
+    // an articulated arm adds finger / palm contacts with the block and the pan (configs[2]: 4 pan-block + up to 4 hand-pan +
+    // up to 4 hand-block were seen along gripper roll-outs)
+    for (int b = 1; b < m.nbody; b++) if (m.body_parent[b] > 0) { m.ncon_max += 4; break; }
     if (m.ncon_max > 32) m.ncon_max = 32;
     int nlim = 0;
     for (int j = 0; j < m.njnt; j++) nlim += m.jnt_limited[j] ? 1 : 0;

@@ -95,17 +95,18 @@ __device__ __noinline__ V3d support(const Tab& t, const Slice& s, const float* v
   const int type = t.geom_type[gi];
   const float* sz = t.geom_size + 3 * gi;
   V3d res;
+  const double tie = -HSR_SUPPORT_TIE;   // support ties: hsr_core.h
   if (type == GEOM_BOX) {
-    res = mk<double>(dl.x >= 0 ? (double)sz[0] : -(double)sz[0], dl.y >= 0 ? (double)sz[1] : -(double)sz[1],
-                     dl.z >= 0 ? (double)sz[2] : -(double)sz[2]);
+    res = mk<double>(dl.x >= tie ? (double)sz[0] : -(double)sz[0], dl.y >= tie ? (double)sz[1] : -(double)sz[1],
+                     dl.z >= tie ? (double)sz[2] : -(double)sz[2]);
   } else if (type == GEOM_CYLINDER) {
     const double n = sqrt(dl.x * dl.x + dl.y * dl.y);
-    res = mk<double>(0, 0, dl.z >= 0 ? (double)sz[1] : -(double)sz[1]);
+    res = mk<double>(0, 0, dl.z >= tie ? (double)sz[1] : -(double)sz[1]);
     if (n > 1e-15) { res.x = dl.x / n * (double)sz[0]; res.y = dl.y / n * (double)sz[0]; }
   } else {
     const DevGrp<32> gw;
     const float* v4 = verts4 + 4 * t.geom_vertadr[gi];
-    const int bi = hull_scan4(reinterpret_cast<const float4*>(v4), t.geom_vertnum[gi], (float)dl.x, (float)dl.y, (float)dl.z, gw);
+    const int bi = hull_argmax<float>(v4, 4, t.geom_vertnum[gi], dl, gw);
     res = mk<double>((double)v4[4 * bi], (double)v4[4 * bi + 1], (double)v4[4 * bi + 2]);
   }
   return ld3(s.gpos + 3 * gi) + mulv(R, res);

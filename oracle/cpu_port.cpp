@@ -18,6 +18,7 @@
 #include <thread>
 #include <vector>
 
+#define HSR_SCAN_NOISE 1
 #include "../hsr_env_b200/csrc/hsr_core.h"
 
 using namespace hsr;
@@ -185,6 +186,9 @@ void hsrp_set_starts(void* hv, int n, const int* adr, const int* width, const do
   set_starts(h->cfgd, n, adr, width, lo, hi);
   set_starts(h->cfgf, n, adr, width, lo, hi);
 }
+
+// fp32-rounding-sized noise on the hull-vertex scans of the calling thread (0 = off): see HSR_SCAN_NOISE in hsr_core.h
+void hsrp_set_scan_noise(unsigned long long seed) { hsr_scan_noise_seed = seed; }
 
 // Step n environments by up to nsub substeps each (teacher-forced from the given states).
 // dbg != NULL: exactly one substep, per-stage dump (debug_size doubles per env).

@@ -214,17 +214,30 @@ def plane_box(ppos, pmat, bpos, bmat, size):
     return out
 
 
+SUPPORT_TIE = 1e-12   # support ties (see support())
+
+
 def support(gtype, size, verts, pos, mat, dirw):
-    """Support point of a convex geom in world direction dirw (mjccd_support, margin 0)."""
+    """Support point of a convex geom in world direction dirw (mjccd_support, margin 0).
+
+    Ties.  A box face / edge perpendicular to the direction, or a hull face whose vertices share the maximal support,
+    is a TIE in exact arithmetic, and such directions are not accidents: the portal refinement converges to face
+    normals of the Minkowski difference, and resting contacts line directions up with box axes.  With plain comparisons
+    (libccd / MuJoCo: `dir[i] > 0`, first maximum of the vertex scan) the winner is decided by rounding noise of order
+    1e-17, differently in every implementation, and the contact point jumps across the face.  This restatement (and the
+    kernels, hsr_core.h support_d) resolves ties DETERMINISTICALLY: a local direction component within SUPPORT_TIE of
+    zero counts as positive, and among the hull vertices whose support is within SUPPORT_TIE of the maximum the lowest
+    index wins.  It only changes results where MuJoCo's own answer is rounding noise."""
     dl = mat.T @ dirw
     if gtype == GEOM_BOX:
-        res = np.where(dl >= 0, 1.0, -1.0) * size
+        res = np.where(dl >= -SUPPORT_TIE, 1.0, -1.0) * size
     elif gtype == GEOM_CYLINDER:
         n = np.hypot(dl[0], dl[1])
         res = np.array([dl[0] / n * size[0], dl[1] / n * size[0], 0.0]) if n > MINVAL else np.zeros(3)
-        res[2] = size[1] if dl[2] >= 0 else -size[1]
+        res[2] = size[1] if dl[2] >= -SUPPORT_TIE else -size[1]
     else:
-        res = verts[np.argmax(verts @ dl)]
+        vals = verts[:, 0] * dl[0] + verts[:, 1] * dl[1] + verts[:, 2] * dl[2]
+        res = verts[int(np.argmax(vals >= vals.max() - SUPPORT_TIE))]
     return pos + mat @ res
 
 

@@ -46,6 +46,7 @@ class CpuPort:
         _ip = ctypes.POINTER(ctypes.c_int)
         lib.hsrp_set_goal_list.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip, _ip, _dp, _dp, _dp, ctypes.c_int]
         lib.hsrp_set_starts.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip, _ip, _dp, _dp]
+        lib.hsrp_set_scan_noise.argtypes = [ctypes.c_ulonglong]
         lib.hsrp_reset.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, _dp, _dp]
         self.lib = lib
         blob = model.to_blob()
@@ -101,6 +102,10 @@ class CpuPort:
         if debug:
             out["debug"] = [unpack_debug(self, dbg[i]) for i in range(n)]
         return out
+
+    def set_scan_noise(self, seed):
+        """fp32-rounding-sized noise on the hull-vertex scans (single-threaded calls of this thread); 0 switches it off"""
+        self.lib.hsrp_set_scan_noise(int(seed))
 
     def reset(self, seed, env_id, episode):
         q = np.zeros(self.nq); mo = np.zeros(3)
