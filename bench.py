@@ -2,20 +2,30 @@
 configuration (BASELINE.json configs[1]: 4096 batched environments per B200, randomized block-space /
 goal-space resets), one process per GPU, weak scaling (4096 environments per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu 4096] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu 4096] [--impl reference] [--no-configs]
 
-A "step" is one env action for every environment of the batch: a masked reset of the environments that
-finished on the previous action (the caller's ``if done: env.reset()``, /root/reference/hsr/control.py:73-75)
-followed by ``HSREnv.step`` (/root/reference/hsr/env.py:115-135) = up to 300 substeps with the per-substep
-goal test and early break.  Executed substeps are counted (``substeps_taken``), never assumed to be 300.
+A "step" is one env action for every environment of the batch: a masked reset of the environments whose episode
+ended on the previous action - success (the caller's ``if done: env.reset()``, /root/reference/hsr/control.py:73-75) or
+the reference's ``TimeLimit(max_episode_steps=20)`` (/root/reference/hsr/__init__.py:22) - followed by ``HSREnv.step``
+(/root/reference/hsr/env.py:115-135) = up to 300 substeps with the per-substep goal test and early break.  Episode ages
+start staggered (env i is i mod 20 actions into its episode), so the mix of episode phases - and with it the work per
+action - is the same on every step.  Executed substeps are counted (``substeps_taken``), never assumed to be 300.
 
-Prints ONE JSON line on rank 0.  ``--impl reference`` times the CPU side instead: the reference's own
-implementation (mujoco-py) cannot run here, so it is the oracle's C++ port on all host cores,
-labelled ``kind: "port"``.
+Both arms run the SAME workload: same Philox reset streams (global env ids), same host-generated actions, same episode
+ages, the same W warm-up actions before the K timed ones.  ``--impl reference`` times the CPU side: the reference's own
+implementation (mujoco-py) cannot run here, so it is the oracle's fp64 C++ port on all host cores,
+labelled ``kind: "port"`` (NOT MuJoCo).
+
+Besides the headline (``value``, configs[1]) the line carries ``configs``: configs[2] (full arm + gripper, 16384 envs,
+gripper-block contact workload), configs[3] (2^20 envs of the block-push model sharded over the N ranks: strong
+scaling) and configs[4] (4-block clutter), each with its own substeps/s, measured flops per substep and FP32 fraction.
+
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -32,18 +42,39 @@ BLOCK_LO, BLOCK_HI = [-.25, -.2, 0., -1.], [-.05, .1, 1., 1.]   # (x, y, qw, qz)
 GOAL_LO, GOAL_HI = [-.15, -.2, .017], [0., .1, .017]
 GEOFENCE = .05
 NSUB = 300
+TIME_LIMIT = 20      # gym.wrappers.TimeLimit(env, max_episode_steps=20), /root/reference/hsr/__init__.py:22
 BLOB = "c2_push.hsrb"
 WORKLOAD = ("c2_push: --use-dof slide_x slide_y --n-blocks 1 --steps-per-action=300 --geofence=.05, "
             "block-space (-.25,-.05)(-.2,.1)(0,1)(-1,1), goal-space (-.15,0)(-.2,.1)(.017,.017), "
-            "actions ~ U(ctrlrange), done envs reset every action")
+            "actions ~ U(ctrlrange), envs reset on success or after 20 actions (TimeLimit), staggered episode ages")
+# configs[2]: block on the pan, hand hovering at block height (start spaces of the arm joints), configs[4]: four blocks
+C3_BLOCK_LO, C3_BLOCK_HI = [-.1, -.18, 0., -1.], [.1, .18, 1., 1.]
+C3_GOAL_LO, C3_GOAL_HI = [-.1, -.18, .422], [.1, .18, .422]
+C3_STARTS = {"slide_x": (-.05, .12), "slide_y": (-.1, .1), "arm_lift_joint": (0., .12), "arm_flex_joint": (-1.9, -1.25),
+             "wrist_roll_joint": (-1.57, 1.57), "hand_l_proximal_joint": (0., .349), "hand_r_proximal_joint": (0., .349)}
+C5_BLOCK_LO, C5_BLOCK_HI = [-.2, -.2, 0., -1.], [.1, .2, 1., 1.]     # 0.3 x 0.4 m patch on the floor in front of the base
+C5_GOAL_LO, C5_GOAL_HI = [-.15, -.2, .017], [.1, .2, .017]
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
-    return 6650.0, 1965.0, "fallback"
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json, burst copy figure)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def host_actions(seed: int, steps: int, n: int, lo, hi, offset: int = 0):
+    """Actions ~ U(ctrlrange) for `steps` actions of environments [offset, offset + n), generated on the host so that both
+    arms (and every rank count) see the same numbers: one Philox stream per step, rows indexed by the global env id."""
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    nu = len(lo)
+    out = np.empty((steps, n, nu), np.float32)
+    for k in range(steps):
+        rng = np.random.Generator(np.random.Philox(key=seed + 7919 * k))
+        u = rng.random(((offset + n) * nu,), dtype=np.float32)[offset * nu:]   # rows of the global env ids
+        out[k] = lo + (hi - lo) * u.reshape(n, nu)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -105,39 +136,45 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
-def cpu_port_run(n_envs: int, n_actions: int, threads: int, seed: int = 0, budget_s: float = 1e9):
-    """The same workload on the oracle's fp64 C++ port (one environment per thread at a time): returns
-    (env_actions, substeps, seconds, algorithmic flops).  Test infrastructure used as a reported baseline only."""
+def cpu_port_run(n_envs: int, warmup: int, steps: int, threads: int, seed: int = 0, budget_s: float = 1e9):
+    """The headline workload on the oracle's fp64 C++ port (one environment per thread at a time), environments
+    [0, n_envs) of the same Philox streams, the same actions and episode ages as the GPU arm; `warmup` untimed actions,
+    then up to `steps` timed ones (stops early when `budget_s` of stepping time is spent).  Returns (env_actions,
+    substeps, seconds, algorithmic flops) of the timed part.  Test infrastructure used as a reported baseline only."""
     from hsr_env_b200.model import Model
     from oracle import port
 
     model = Model.load(ROOT / "hsr_env_b200" / "blobs" / BLOB)
     cp = port.CpuPort(model)
     cp.set_goals(np.r_[GOAL_LO, GOAL_HI], np.r_[BLOCK_LO, BLOCK_HI], GEOFENCE)
-    rng = np.random.default_rng(seed)
     qpos = np.zeros((n_envs, model.nq)); mocap = np.zeros((n_envs, 3))
     episode = np.zeros(n_envs, np.int64)
     for e in range(n_envs):
         qpos[e], mocap[e] = cp.reset(seed, e, 0)
     qvel = np.zeros((n_envs, model.nv)); warm = np.zeros((n_envs, model.nv))
-    lo, hi = model.act_ctrlrange[:, 0], model.act_ctrlrange[:, 1]
+    age = np.arange(n_envs) % TIME_LIMIT
+    done = np.zeros(n_envs, bool)
+    acts = host_actions(seed, warmup + steps, n_envs, model.act_ctrlrange[:, 0], model.act_ctrlrange[:, 1])
     actions = substeps = flops = 0
     t_total = 0.0
-    for a in range(n_actions):
-        ctrl = rng.uniform(lo, hi, size=(n_envs, model.nu))
+    for a in range(warmup + steps):
         t0 = time.perf_counter()
-        out = cp.step(qpos, qvel, warm, ctrl, mocap, nsub=NSUB, nthreads=threads)
-        t_total += time.perf_counter() - t0
-        qpos, qvel, warm = out["qpos"], out["qvel"], out["warm"]
-        actions += n_envs
-        substeps += int(out["taken"].sum())
-        flops += int(out["counters"][:, 3].sum())
-        for e in np.nonzero(out["success"])[0]:
+        for e in np.nonzero(done | (age >= TIME_LIMIT))[0]:
             episode[e] += 1
             qpos[e], mocap[e] = cp.reset(seed, int(e), int(episode[e]))
-            qvel[e] = 0; warm[e] = 0
-        if t_total > budget_s:
-            break
+            qvel[e] = 0; warm[e] = 0; age[e] = 0
+        out = cp.step(qpos, qvel, warm, acts[a].astype(np.float64), mocap, nsub=NSUB, nthreads=threads)
+        dt = time.perf_counter() - t0
+        qpos, qvel, warm = out["qpos"], out["qvel"], out["warm"]
+        done = out["success"].astype(bool)
+        age += 1
+        if a >= warmup:
+            t_total += dt
+            actions += n_envs
+            substeps += int(out["taken"].sum())
+            flops += int(out["counters"][:, 3].sum())
+            if t_total > budget_s:
+                break
     return actions, substeps, t_total, flops
 
 
@@ -146,20 +183,21 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_envs = max(cores * 32, 256)
-    # warm-up + timed "steps": each step = one action for a bounded sample of n_envs environments (of the 4096)
-    cpu_port_run(n_envs, max(1, min(args.warmup, 2)), cores)
-    acts, subs, secs, flops = cpu_port_run(n_envs, args.steps, cores, budget_s=120.0)
+    n_envs = args.envs_per_gpu      # the whole configuration, not a sub-sample: ~0.4 s per action on 16 threads
+    acts, subs, secs, flops = cpu_port_run(n_envs, args.warmup, args.steps, cores, seed=args.seed, budget_s=150.0)
     value = acts / secs
+    done_steps = acts // n_envs
     line = {
         "impl": "reference", "metric": "env_actions_per_sec", "value": value, "unit": "env-actions/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, acts / n_envs),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, done_steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": n_envs},
-        "substeps_per_s": subs / secs, "mean_substeps_per_action": subs / acts,
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n_envs, "total_envs": n_envs, "substeps_per_action": NSUB,
+                   "time_limit": TIME_LIMIT},
+        "substeps_per_s": subs / secs, "mean_substeps_per_action": subs / max(1, acts),
         "cpu_baseline": {"value": value, "unit": "env-actions/s", "cores": cores, "kind": "port",
-                         "sample": f"{acts} env-actions ({subs} substeps) of the workload on {cores} threads; the "
-                                   "reference's mujoco-py cannot be installed here, this is the oracle's fp64 C++ port, NOT MuJoCo"},
+                         "sample": f"{done_steps} of {args.steps} timed actions of all {n_envs} environments ({subs} substeps, {secs:.1f} s) "
+                                   f"after {args.warmup} warm-up actions, {cores} host threads; the reference's mujoco-py cannot be "
+                                   "installed here: this is the oracle's fp64 C++ port (our own restatement), NOT MuJoCo"},
         "e2e": {"value": value, "unit": "env-actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,11 +205,133 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU side
+def fp32_peak(device_index: int) -> float:
+    from hsr_env_b200 import lib as L
+
+    v = ctypes.c_double()
+    L.check(L.load().hsrb_measure_fp32_peak(device_index, ctypes.byref(v)))
+    return float(v.value)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def run_workload(torch, D, dev, *, blob, goals, starts, n_local, env_offset, steps, warmup, seed, kernel="auto",
+                 lanes=0, min_sep=0.0, flush=None, time_limit=TIME_LIMIT, sampler=None):
+    """`warmup` untimed + `steps` timed actions of one configuration on this rank's slice [env_offset, env_offset +
+    n_local) of the global environments.  Returns a dict with device-timed seconds (max over ranks), substeps, flops,
+    contacts, launch info and the env (open, for follow-up legs)."""
+    from hsr_env_b200.env import BatchedHSREnv
+
+    env = BatchedHSREnv(blob, goals, starts=starts, steps_per_action=NSUB, n_envs=n_local, device=dev, seed=seed,
+                        env_id_offset=env_offset, lanes_per_env=lanes, kernel=kernel, min_block_separation=min_sep)
+    info = env.launch_info()
+    acts_h = host_actions(seed, warmup + steps, n_local, env.model.act_ctrlrange[:, 0], env.model.act_ctrlrange[:, 1], offset=env_offset)
+    actions = torch.from_numpy(acts_h).to(dev)
+    env.reset()
+    age = ((torch.arange(n_local, device=dev) + env_offset) % time_limit).to(torch.int32)
+    done = torch.zeros(n_local, dtype=torch.bool, device=dev)
+    taken_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    succ_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    reset_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    kstart = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    kend = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+
+    def one_step(k, timed=None):
+        nonlocal done, age, reset_sum
+        mask = done | (age >= time_limit)
+        env.reset(mask=mask)
+        age = torch.where(mask, torch.zeros_like(age), age)
+        if timed is not None:
+            reset_sum += mask.sum()
+            kstart[timed].record()   # the action kernel alone (torch's current stream = the launching stream)
+        obs, reward, done, inf = env.step(actions[k])
+        if timed is not None:
+            kend[timed].record()
+        age = age + 1
+        return inf["substeps_taken"]
+
+    for k in range(warmup):
+        one_step(k)
+    torch.cuda.synchronize(dev)
+    st0 = env.stats()
+    starts_ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends_ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    D.barrier()
+    torch.cuda.synchronize(dev)
+    snap = [t.clone() for t in env.get_state()] + [done.clone(), age.clone()]
+    with (sampler if sampler is not None else _Null()):
+        for k in range(steps):
+            if flush is not None:
+                flush.fill_(k & 0xff)           # evict L2 between timed iterations (outside the event bracket)
+            starts_ev[k].record()
+            taken = one_step(warmup + k, timed=k)
+            ends_ev[k].record()
+            taken_sum += taken.sum()
+            succ_sum += done.sum()
+        torch.cuda.synchronize(dev)
+    D.barrier()
+    secs = sum(s.elapsed_time(e) for s, e in zip(starts_ev, ends_ev)) * 1e-3
+    kernel_s = sum(s.elapsed_time(e) for s, e in zip(kstart, kend)) * 1e-3 / steps   # mean action-kernel launch
+    st1 = env.stats()
+    secs_max = D.max_over_ranks(secs, dev)
+    d = {k: float(st1[k] - st0[k]) for k in ("substeps", "flops", "contacts", "efc_rows", "newton_iters", "bad_envs", "launches")}
+    tot = D.sum_over_ranks([float(taken_sum.item()), float(succ_sum.item()), d["bad_envs"], d["flops"], d["contacts"], d["newton_iters"],
+                            float(reset_sum.item())], dev)
+    return dict(env=env, info=info, secs=secs_max, kernel_s=kernel_s, substeps=tot[0], successes=tot[1], bad=tot[2], flops=tot[3],
+                contacts=tot[4], iters=tot[5], resets=tot[6], launches=int(d["launches"]), snap=snap, actions_host=acts_h,
+                local_substeps=float(taken_sum.item()), local_successes=float(succ_sum.item()), local_bad=d["bad_envs"],
+                stats0=st0, stats1=st1)
+
+
+def config_entry(r, n_total, steps, peak_tf, world, extra=None):
+    """Throughput / roofline entry of one configuration."""
+    sub_s = r["substeps"] / r["secs"]
+    f_alg = r["flops"] / max(1.0, r["substeps"])
+    tf = r["flops"] / r["secs"] / 1e12 / world
+    e = {"envs_total": n_total, "steps": steps, "env_actions_per_s": n_total * steps / r["secs"], "substeps_per_s": sub_s,
+         "substeps_per_s_per_gpu": sub_s / world, "ms_per_step": 1e3 * r["secs"] / steps,
+         "mean_substeps_per_action": r["substeps"] / (n_total * steps), "mean_flops_per_substep": f_alg,
+         "mean_contacts_per_substep": r["contacts"] / max(1.0, r["substeps"]),
+         "mean_newton_iters_per_substep": r["iters"] / max(1.0, r["substeps"]),
+         "fp32_tflops_per_gpu": tf, "fp32_frac": tf / peak_tf, "bad_states": r["bad"],
+         "success_per_action": r["successes"] / (n_total * steps), "resets_per_action": r["resets"] / (n_total * steps),
+         "kernel": r["info"]["kernel"], "lanes_per_env": r["info"]["lanes_per_env"], "threads_per_block": r["info"]["threads_per_block"],
+         "grid": r["info"]["grid"], "smem_per_env": r["info"]["smem_per_env"], "resident_envs_per_sm": r["info"]["envs_per_sm"]}
+    if extra:
+        e.update(extra)
+    return e
+
+
+def regime_census(env, blob_name, n_sample=256):
+    """What kinds of contacts the states of a run hold (oracle port on a host copy of `n_sample` states, outside every
+    timed region): evidence that configs[2] really is in the gripper-block regime."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from hsr_env_b200.model import Model
+    from oracle import port
+    from scenarios import regimes
+
+    model = Model.load(ROOT / "hsr_env_b200" / "blobs" / blob_name)
+    cp = port.CpuPort(model)
+    cp.set_caps(64, 64 * 6 + 8)
+    qpos, qvel, warm, _ = [t[:n_sample].double().cpu().numpy() for t in env.get_state()]
+    dbg = cp.step(qpos, qvel, warm, np.zeros((len(qpos), model.nu)), nsub=1, debug=True)["debug"]
+    counts = {}
+    for d in dbg:
+        for r in regimes(model, d):
+            counts[r] = counts.get(r, 0) + 1
+    return {k: v / len(dbg) for k, v in sorted(counts.items())}
+
+
 def run_gpu(args):
     import torch
 
     from hsr_env_b200 import dist as D
-    from hsr_env_b200.env import BatchedHSREnv
     from hsr_env_b200.spaces import Box
     from hsr_env_b200.util import GoalSpec
 
@@ -181,88 +341,44 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     n = args.envs_per_gpu
-    goals = [GoalSpec(a=Box(BLOCK_LO, BLOCK_HI), b=Box(GOAL_LO, GOAL_HI), distance=GEOFENCE)]
-    env = BatchedHSREnv(BLOB, goals, steps_per_action=NSUB, n_envs=n, device=dev, seed=args.seed,
-                        env_id_offset=rank * n, lanes_per_env=args.lanes, kernel=args.kernel)
-    info = env.launch_info()
-    lo = torch.tensor(env.model.act_ctrlrange[:, 0], dtype=torch.float32, device=dev)
-    hi = torch.tensor(env.model.act_ctrlrange[:, 1], dtype=torch.float32, device=dev)
-    gen = torch.Generator(device=dev).manual_seed(args.seed + 1000 * rank)
-    total = args.warmup + args.steps
-    actions = [lo + (hi - lo) * torch.rand(n, env.nu, generator=gen, device=dev) for _ in range(total)]
-    if args.action_scale != 1.0:   # experiments only (e.g. 0 = the robot stands still: floor contacts only)
-        actions = [a * args.action_scale for a in actions]
+    peak_tf = fp32_peak(local)       # FMA-loop peak of THIS device, measured in this run
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    goals = [GoalSpec(a=Box(BLOCK_LO, BLOCK_HI), b=Box(GOAL_LO, GOAL_HI), distance=GEOFENCE)]
 
-    env.reset()
-    done = torch.zeros(n, dtype=torch.bool, device=dev)
-    taken_sum = torch.zeros((), dtype=torch.int64, device=dev)
-    succ_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    # ---------------------------------------------------------------- headline: configs[1], weak scaling
+    clk = ClockSampler(local)
+    r = run_workload(torch, D, dev, blob=BLOB, goals=goals, starts=None, n_local=n, env_offset=rank * n,
+                     steps=args.steps, warmup=args.warmup, seed=args.seed, kernel=args.kernel, lanes=args.lanes, flush=flush,
+                     sampler=clk)
+    env, info = r["env"], r["info"]
+    gathered = D.gather_episode_stats(dict(episodes=r["local_successes"], successes=r["local_successes"],
+                                           substeps=r["local_substeps"], bad_states=r["local_bad"]), dev)
 
-    kstart = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kend = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-
-    def one_step(k, timed=None):
-        nonlocal done
-        env.reset(mask=done)
-        if timed is not None:
-            kstart[timed].record()   # the action kernel alone (torch's current stream = the launching stream)
-        obs, reward, done, inf = env.step(actions[k])
-        if timed is not None:
-            kend[timed].record()
-        return inf["substeps_taken"]
-
-    for k in range(args.warmup):
-        one_step(k)
-    torch.cuda.synchronize(dev)
-    st0 = env.stats()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    D.barrier()
-    torch.cuda.synchronize(dev)
-    # the workload drifts along the episodes (blocks get pushed away from the base: 36 -> 23 ms per action over 60
-    # actions, tools/step_time_trend.py), so the end-to-end leg below restarts from this snapshot: both legs time the
-    # same actions on the same states
-    snap = [t.clone() for t in env.get_state()] + [done.clone()]
-    with ClockSampler(local) as clk:
-        for k in range(args.steps):
-            flush.fill_(k & 0xff)           # evict L2 between timed iterations (outside the event bracket)
-            starts[k].record()
-            taken = one_step(args.warmup + k, timed=k)
-            ends[k].record()
-            taken_sum += taken.sum()
-            succ_sum += done.sum()
-        torch.cuda.synchronize(dev)
-    D.barrier()
-    secs = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
-    kernel_s = sum(s.elapsed_time(e) for s, e in zip(kstart, kend)) * 1e-3 / args.steps   # mean action-kernel launch
-    st1 = env.stats()
-    secs_max = D.max_over_ranks(secs, dev)
-    sub_local = float(taken_sum.item())
-    sub_total, succ_total, bad_total = D.sum_over_ranks([sub_local, float(succ_sum.item()), float(st1["bad_envs"] - st0["bad_envs"])], dev)
-    flops_local = st1["flops"] - st0["flops"]
-    flops_total = D.sum_over_ranks([float(flops_local)], dev)[0]
-    launches = st1["launches"] - st0["launches"]
-    gathered = D.gather_episode_stats(dict(episodes=float(succ_sum.item()), successes=float(succ_sum.item()),
-                                           substeps=sub_local, bad_states=float(st1["bad_envs"] - st0["bad_envs"])), dev)
-
-    # ---- end to end through the host-buffer API: pinned host actions in, obs/reward/done/substeps out, every step
+    # ---- end to end through the host-buffer API: pinned host actions in, obs/reward/done/substeps out, every step,
+    #      restarted from the snapshot taken before the timed steps: the same actions on the same states
     e2e_steps = args.steps
-    act_host = [a.cpu().pin_memory() for a in actions[args.warmup:args.warmup + e2e_steps]]
+    act_host = [torch.from_numpy(r["actions_host"][args.warmup + k]).pin_memory() for k in range(e2e_steps)]
     out = dict(obs=torch.empty(n, env.obs_dim).pin_memory(), reward=torch.empty(n).pin_memory(),
                done=torch.zeros(n, dtype=torch.uint8).pin_memory(), taken=torch.empty(n, dtype=torch.int32).pin_memory())
+    mask_host = torch.zeros(n, dtype=torch.uint8).pin_memory()
     mask_dev = torch.zeros(n, dtype=torch.uint8, device=dev)
+    snap = r["snap"]
     for k in range(min(3, e2e_steps)):  # warm-up of the host path
         env.step_host(act_host[k], out=out)
     env.set_state(qpos=snap[0], qvel=snap[1], qacc_warmstart=snap[2], mocap_pos=snap[3])
     out["done"].copy_(snap[4].to(torch.uint8))
+    age_h = snap[5].cpu().numpy().copy()
     D.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        mask_dev.copy_(out["done"], non_blocking=True)            # H2D: which environments the caller resets
+        m = (out["done"].numpy() != 0) | (age_h >= TIME_LIMIT)      # the caller's bookkeeping, on the host
+        mask_host.numpy()[:] = m
+        age_h[m] = 0
+        mask_dev.copy_(mask_host, non_blocking=True)              # H2D: which environments the caller resets
         env.reset(mask=mask_dev)
         env.step_host(act_host[k], out=out)                       # H2D ctrl, kernel, D2H obs/reward/done/taken, sync
+        age_h += 1
     torch.cuda.synchronize(dev)
     e2e_secs = D.max_over_ranks(time.perf_counter() - t0, dev)
     h2d = n * env.nu * 4 + n
@@ -272,57 +388,112 @@ def run_gpu(args):
     nq, nv, nu = env.nq, env.nv, env.nu
     # algorithmic HBM bytes per env-action: state in/out once per action
     b_alg = 4 * ((nq + 2 * nv + nu + 3 + 2) + (nq + 2 * nv + (nq + nv) + 4))
-    achieved_gbs = b_alg * n / kernel_s / 1e9
+    achieved_gbs = b_alg * n / r["kernel_s"] / 1e9
     traffic = None
     tp = ROOT / "profiles" / "r01_traffic.json"
     if tp.exists() and n == 4096 and info["kernel"] == "fast":
         traffic = json.loads(tp.read_text())["dram_bytes_per_launch"]
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     clocks = clk.summary()
-    fp32_peak_at_clock = fp32_peak * (clocks["sm_mhz"] / sm_max) if clocks.get("sm_mhz") else None
-    achieved_tf = flops_total / secs_max / 1e12 / world
+    secs_max = r["secs"]
+    achieved_tf = r["flops"] / secs_max / 1e12 / world
+    f_alg = r["flops"] / max(1.0, r["substeps"])
     value = world * n * args.steps / secs_max
+    kname = {"fast": "hsrb_push_kernel", "wpe": "hsrb_wpe_kernel"}.get(info["kernel"], "hsrb_step_kernel")
     line = {
         "metric": "env_actions_per_sec", "value": value, "unit": "env-actions/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": n * world, "substeps_per_action": NSUB,
-                   "l2": "flushed (256 MiB write) between timed steps", "kernel": info["kernel"], "threads_per_block": info["threads_per_block"], "lanes_per_env": info["lanes_per_env"],
+                   "time_limit": TIME_LIMIT, "l2": "flushed (256 MiB write) between timed steps", "kernel": info["kernel"],
+                   "threads_per_block": info["threads_per_block"], "lanes_per_env": info["lanes_per_env"],
                    "smem_per_env": info["smem_per_env"], "resident_envs_per_sm": info["envs_per_sm"], "grid": info["grid"]},
-        "substeps_per_s": sub_total / secs_max, "mean_substeps_per_action": sub_total / (world * n * args.steps),
-        "success_per_action": succ_total / (world * n * args.steps), "bad_states": bad_total,
-        "clocks": clocks,
+        "substeps_per_s": r["substeps"] / secs_max, "mean_substeps_per_action": r["substeps"] / (world * n * args.steps),
+        "success_per_action": r["successes"] / (world * n * args.steps), "resets_per_action": r["resets"] / (world * n * args.steps),
+        "bad_states": r["bad"], "clocks": clocks,
         "e2e": {"value": world * n * e2e_steps / e2e_secs, "unit": "env-actions/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "substeps_per_s": None},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": which + " (burst copy figure)",
-                     "kernel": "hsrb_push_kernel" if info["kernel"] == "fast" else "hsrb_step_kernel",
-                     "kernel_ms_per_launch": 1e3 * kernel_s, "algorithmic_bytes_per_launch": b_alg * n,
-                     "algorithmic_bytes_per_env_action": b_alg,
-                     "note": "state crosses HBM once per action (312 B per env-action): this path is bound by the instruction "
-                             "stream of a warp (issue / fetch latency), not by HBM or the FP32 pipe; see fp32 and DESIGN.md 4.1"},
-        "fp32": {"achieved_tflops": achieved_tf, "peak_tflops_at_max_clock": fp32_peak,
-                 "peak_tflops_at_observed_clock": fp32_peak_at_clock,
-                 "frac_of_max_clock_peak": achieved_tf / fp32_peak,
-                 "mean_algorithmic_flops_per_substep": flops_total / max(1.0, sub_total),
-                 "note": "algorithmic flops = SURVEY.md 8(d) stage formulas with the kernel's actual per-substep counts"},
+        "gpu_launches": int(r["launches"]),
+        # the binding ceiling of this path is the FP32 (CUDA-core) pipe, not HBM
+        "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": traffic,
+                     "traffic_source": ("static: dram__bytes_read+write of one ncu --set full capture of this kernel and batch, "
+                                        "profiles/r01_traffic.json; not measured in this run") if traffic is not None else None,
+                     "peak_source": "FP32 FMA-loop peak measured in this run (hsrb_measure_fp32_peak: 8 FMA chains x 1024 threads x 2 blocks per SM)",
+                     "kernel": kname, "kernel_ms_per_launch": 1e3 * r["kernel_s"],
+                     "algorithmic_flops_per_substep": f_alg,
+                     "algorithmic_flops_per_launch": r["flops"] / world / args.steps,
+                     "note": "achieved = substeps/s x mean algorithmic flops per substep (SURVEY.md 8(d) stage formulas evaluated by the "
+                             "kernel with the actual per-substep contact / row / iteration counts) per GPU; the kernel is bound by "
+                             "dependent-instruction latency and instruction fetch, see DESIGN.md 4.1"},
+        "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": hbm_peak, "frac": achieved_gbs / hbm_peak, "peak_source": which,
+                "algorithmic_bytes_per_launch": b_alg * n, "algorithmic_bytes_per_env_action": b_alg,
+                "note": "state crosses HBM once per action; HBM is not the bound of this path"},
         "episode_stats_per_rank": gathered,
     }
-    ph = {k: st1["phase_cycles"][k] - st0["phase_cycles"][k] for k in st1["phase_cycles"]}
+    ph = {k: r["stats1"]["phase_cycles"][k] - r["stats0"]["phase_cycles"][k] for k in r["stats1"]["phase_cycles"]}
     if sum(ph.values()) > 0:
         tot = float(sum(ph.values()))
         line["phase_share"] = {k: round(v / tot, 4) for k, v in ph.items()}
-        line["phase_cycles_per_substep_lane0"] = tot / max(1.0, sub_local)
+        line["phase_cycles_per_substep_lane0"] = tot / max(1.0, r["local_substeps"])
+    env.close()
+    del flush
+
+    # ---------------------------------------------------------------- the other BASELINE.json configs
+    if not args.no_configs:
+        cfgs = {}
+        # configs[3]: 2^20 environments of the block-push model sharded over the ranks (strong scaling)
+        n4 = args.c4_envs // world
+        r4 = run_workload(torch, D, dev, blob=BLOB, goals=goals, starts=None, n_local=n4, env_offset=rank * n4,
+                          steps=1, warmup=1, seed=args.seed + 1, kernel=args.kernel)
+        cfgs["c4_1m_envs_sharded"] = config_entry(r4, n4 * world, 1, peak_tf, world, {
+            "workload": f"configs[3]: {n4 * world} environments of the block-push model, {n4} per GPU on {world} GPU(s) (contiguous slices of "
+                        "the global env ids, no data-path collective); 1 warm-up + 1 timed action", "scaling": "strong"})
+        r4["env"].close()
+        # configs[2] and configs[4]: every rank runs its own batch (weak)
+        c3_starts = {k: Box([lo], [hi]) for k, (lo, hi) in C3_STARTS.items()}
+        c3_goals = [GoalSpec(a=Box(C3_BLOCK_LO, C3_BLOCK_HI), b=Box(C3_GOAL_LO, C3_GOAL_HI), distance=GEOFENCE)]
+        n3 = args.c3_envs
+        # under U(ctrlrange) the position servos lift the arm off the pan within ~50 substeps (arm_lift's target lies above
+        # its range, arm_flex's at >= -1.2 rad), so the gripper contacts live at the start of an episode: one action per
+        # episode here (TimeLimit 1), every action starts with the hand on / above the block
+        r3 = run_workload(torch, D, dev, blob="c3_arm.hsrb", goals=c3_goals, starts=c3_starts, n_local=n3,
+                          env_offset=rank * n3, steps=2, warmup=1, seed=args.seed + 2, time_limit=1)
+        census = None
+        if rank == 0:
+            e3 = r3["env"]
+            e3.reset()
+            e3.step(torch.from_numpy(r3["actions_host"][0]).to(dev), steps=15)
+            census = regime_census(e3, "c3_arm.hsrb")
+        cfgs["c3_arm_gripper"] = config_entry(r3, n3 * world, 2, peak_tf, world, {
+            "workload": f"configs[2]: full arm + gripper (nv = 13), {n3} environments per GPU, block on the pan (block-space over the pan), "
+                        "hand starting at block height above it (start spaces of the seven robot joints), actions ~ U(ctrlrange), "
+                        "every environment reset before every action (episodes of one action: the servos lift the arm off the pan "
+                        "within ~50 substeps); 1 warm-up + 2 timed actions of 300 substeps",
+            "contact_regimes_fraction_of_states_at_substep_15": census, "scaling": "weak"})
+        r3["env"].close()
+        c5_goals = [GoalSpec(a=Box(C5_BLOCK_LO, C5_BLOCK_HI), b=Box(C5_GOAL_LO, C5_GOAL_HI), distance=GEOFENCE)]
+        n5 = args.c5_envs
+        r5 = run_workload(torch, D, dev, blob="c5_clutter.hsrb", goals=c5_goals, starts=None, n_local=n5,
+                          env_offset=rank * n5, steps=1, warmup=1, seed=args.seed + 3, min_sep=.115)
+        census5 = regime_census(r5["env"], "c5_clutter.hsrb") if rank == 0 else None
+        cfgs["c5_clutter"] = config_entry(r5, n5 * world, 1, peak_tf, world, {
+            "workload": f"configs[4]: slide_x/slide_y base + 4 blocks (nv = 26), {n5} environments per GPU, blocks ~ U over a 0.3 x 0.4 m patch in "
+                        "front of the base, rejection-sampled 11.5 cm apart; 1 warm-up + 1 timed action",
+            "contact_regimes_fraction_of_states": census5, "scaling": "weak"})
+        r5["env"].close()
+        line["configs"] = cfgs
+
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        acts, subs, csecs, _ = cpu_port_run(max(cores * 4, 32), 1000, cores, budget_s=args.cpu_seconds)
+        # the same actions of the same environments after the same warm-up: the first `n_cpu` environments, bounded by time
+        n_cpu = min(n, max(cores * 32, 256))
+        acts, subs, csecs, _ = cpu_port_run(n_cpu, args.warmup, args.steps, cores, seed=args.seed, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {
             "value": acts / csecs, "unit": "env-actions/s", "cores": cores, "kind": "port",
             "substeps_per_s": subs / csecs,
-            "sample": f"{acts} env-actions ({subs} substeps, {csecs:.1f} s) of the same workload on {cores} host threads, "
-                      "oracle fp64 C++ port (NOT mujoco-py: it cannot be installed here)"}
-    env.close()
+            "sample": f"environments 0..{n_cpu - 1} of the same workload (same reset streams, actions, episode ages), {acts // n_cpu} timed actions after "
+                      f"{args.warmup} warm-up actions ({subs} substeps, {csecs:.1f} s) on {cores} host threads; oracle fp64 C++ port (our own "
+                      "restatement, NOT mujoco-py: it cannot be installed here)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -341,7 +512,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--action-scale", type=float, default=1.0, help="experiments: scale the sampled actions")
+    ap.add_argument("--no-configs", action="store_true", help="skip configs[2], [3], [4]")
+    ap.add_argument("--c3-envs", type=int, default=16384)
+    ap.add_argument("--c4-envs", type=int, default=1 << 20, help="total over all ranks")
+    ap.add_argument("--c5-envs", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -22,7 +22,7 @@
 cudaError_t hsrb_push_prepare(int G, int nv, size_t smem, int threads, int* bps);
 cudaError_t hsrb_push_launch(int G, int nv, const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s);
 cudaError_t hsrb_wpe_prepare(size_t smem, int threads, int* bps);
-cudaError_t hsrb_wpe_launch(const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s);
+cudaError_t hsrb_wpe_launch(const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s, bool lock);
 
 namespace {
 
@@ -226,7 +226,8 @@ int run(hsrb* h, KArgs& a, void* stream) {
     a.ws_bytes = h->wpe_ws;
     a.m.ncon_max = WPE_MAXCON; a.m.nefc_max = WPE_MAXROW;
     const size_t smem = (size_t)h->wpe_ws * (h->wpe_threads / 32) + wpe::shared_tail(h->dm);
-    CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream));
+    const char* lk = getenv("HSRB_WPE_LOCK");   // phase-locked variant of the warp-per-environment kernel
+    CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream, lk && lk[0] == '1'));
     h->launches++;
     return 0;
   }
@@ -249,6 +250,19 @@ int run(hsrb* h, KArgs& a, void* stream) {
   CU(launch(h->lanes, a, h->grid, smem, (cudaStream_t)stream));
   h->launches++;
   return 0;
+}
+
+// FP32 FMA-loop peak of the device (the denominator of bench.py's FP32 roofline): 8 independent chains per thread
+__global__ void __launch_bounds__(1024) fma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
 __global__ void gather_state(const float* __restrict__ st, int n, int S, int off, int w, float* __restrict__ out) {
@@ -555,6 +569,34 @@ int hsrb_stats(hsrb_t* h, int64_t* out9, void* stream) {
   CU(cudaMemcpy(v, h->d_stats, sizeof(v), cudaMemcpyDeviceToHost));
   for (int i = 0; i < ST_COUNT; i++) out9[i] = (int64_t)v[i];
   out9[ST_LAUNCHES] = h->launches;
+  return 0;
+}
+
+int hsrb_measure_fp32_peak(int device, double* tflops_out) {
+  if (!tflops_out) return fail(-1, "bad arguments");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 4096;
+  float* out = nullptr;
+  CU(cudaMalloc(&out, sizeof(float) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, 0);
+    fma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  CU(cudaGetLastError());
+  *tflops_out = best;
   return 0;
 }
 

@@ -4,12 +4,14 @@
 #include "hsrb_wpe.cuh"
 
 cudaError_t hsrb_wpe_prepare(size_t smem, int threads, int* bps) {
-  cudaError_t e = cudaFuncSetAttribute(hsrb_wpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(hsrb_wpe_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hsrb_wpe_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, hsrb_wpe_kernel, threads, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, hsrb_wpe_kernel_t<false>, threads, smem);
 }
 
-cudaError_t hsrb_wpe_launch(const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s) {
-  hsrb_wpe_kernel<<<grid, threads, smem, s>>>(a, f);
+cudaError_t hsrb_wpe_launch(const KArgs& a, const PushInfo& f, int grid, int threads, size_t smem, cudaStream_t s, bool lock) {
+  if (lock) hsrb_wpe_kernel_t<true><<<grid, threads, smem, s>>>(a, f);
+  else hsrb_wpe_kernel_t<false><<<grid, threads, smem, s>>>(a, f);
   return cudaGetLastError();
 }

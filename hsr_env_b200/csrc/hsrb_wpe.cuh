@@ -27,6 +27,7 @@
 #define WPE_MAXBG 2                        // geoms riding on the block
 #define WPE_MAXGEOM 24                     // capacities of the fixed shared-memory layout (c2_push: 18 geoms, 21 pairs)
 #define WPE_MAXPAIR 24
+#define WPE_ENVJOBS 8                      // phase-locked variant: convex-convex jobs an environment can queue per substep
 #ifndef WPE_MAXWARPS
 #define WPE_MAXWARPS 28
 #endif
@@ -44,7 +45,7 @@ struct alignas(16) Tab {   // block-shared model tables (one copy per block)
   float geom_rbound[WPE_MAXGEOM];
   float geom_size[WPE_MAXGEOM * 3];
   float pair_friction[WPE_MAXPAIR * 5];
-  float geom_mat[WPE_MAXGEOM * 9];
+  float bgeom_mat[WPE_MAXBG * 9];            // geom_mat (body frame) of the geoms riding on the block
   float geom_aabb[WPE_MAXGEOM * 3];
   int gmove[WPE_MAXGEOM], geom_type[WPE_MAXGEOM], geom_vertadr[WPE_MAXGEOM], geom_vertnum[WPE_MAXGEOM];
   int pair_geom1[WPE_MAXPAIR], pair_geom2[WPE_MAXPAIR], pair_func[WPE_MAXPAIR], pair_condim[WPE_MAXPAIR];
@@ -54,19 +55,28 @@ struct alignas(16) Tab {   // block-shared model tables (one copy per block)
 struct alignas(16) Slice {   // per-warp (= per-environment) slice
   double xb[4], Rb[10], bmat[9 * WPE_MAXBG], gpos[WPE_MAXGEOM * 3], portal[46], mres[8];
   float qpos[12], qvel[8], warm[8], mocap[4], ctrl[4];
-  float gaabb[WPE_MAXGEOM * 3];
+  float baabb[4 * WPE_MAXBG];                                  // world AABB half extents of the block geoms (the others: Tab::ghalf)
   float qs[8], as[8], x[8], qfc[8], srch[8];
   float con_dist[WPE_MAXCON], con_pos[WPE_MAXCON * 3], con_frame[WPE_MAXCON * 9];
-  int con_pair[WPE_MAXCON], con_adr[WPE_MAXCON], wi[WI_COUNT];
+  int con_pair[WPE_MAXCON], con_adr[WPE_MAXCON], wi[4];
+  float jres[WPE_ENVJOBS * 14];                                // phase-locked variant: results of this environment's convex-convex jobs (hit, dist, pos, frame)
   float J[WPE_SLOTS * 8];                                       // 32-byte Jacobian rows
-  float Dr[64], aref[64], rsc[64], jar[64], jv[64], f[64], wrow[64];   // per row slot (rsc: mu on row 0, friction[j-1] on row j)
-  float PQ[16 * WPE_GROUPS], wpq[24], L[64];
+  float Dr[WPE_SLOTS], aref[WPE_SLOTS], rsc[WPE_SLOTS], jar[WPE_SLOTS], jv[WPE_SLOTS], f[WPE_SLOTS], wrow[WPE_SLOTS];   // per row slot (rsc: mu on row 0, friction[j-1] on row j)
+  float PQ[16 * WPE_GROUPS], wpq[2 * WPE_GROUPS + 4], L[64];
   float sep[4 * WPE_MAXPAIR];
 };
 
+// phase-locked variant: block-shared queue of the convex-convex narrowphase jobs of the block's environments; long jobs
+// (no cached separating direction: a full portal refinement) fill it from the front, quick ones from the back, the warps
+// pop from the front
+struct alignas(16) Queue {
+  int cnt[4];                                 // [0] long jobs, [1] quick jobs, [2] next to serve
+  int jobs[WPE_MAXWARPS * WPE_ENVJOBS];       // (owner warp << 16) | (slot << 8) | pair
+};
+
 __host__ __device__ inline size_t slice_bytes() { return sizeof(Slice); }
-// block-shared tail after the slices: the tables, then the hull vertices as float4
-__host__ __device__ inline size_t shared_tail(const ModelT<float>& m) { return sizeof(Tab) + (size_t)m.nvert * 16 + 16; }
+// block-shared tail after the slices: the tables, the job queue, then the hull vertices as float4
+__host__ __device__ inline size_t shared_tail(const ModelT<float>& m) { return sizeof(Tab) + sizeof(Queue) + (size_t)m.nvert * 16 + 16; }
 
 }  // namespace wpe
 
@@ -89,6 +99,7 @@ __device__ __forceinline__ const double* geom_mat(const Tab& t, const Slice& s, 
 
 // support point of geom gi along d (world frame); hull scan in fp32 over the 32 lanes, everything else in double
 // (same arithmetic as hsr::support_d)
+// (s: the slice of the environment the geom belongs to)
 __device__ __noinline__ V3d support(const Tab& t, const Slice& s, const float* verts4, int gi, int gb0, V3d d) {
   const double* R = geom_mat(t, s, gi, gb0);
   const V3d dl = multv(R, d);
@@ -125,15 +136,17 @@ __device__ __forceinline__ void pcopy(Slice& s, int dst, int src) {
 // hsr::mpr_penetration_inl, restructured around ONE support evaluation site (a state machine) with the portal in shared
 // memory: a few hundred instructions of code and a handful of live doubles instead of five 9-double vertices in
 // registers.  `sep`: cached separating direction of the pair (see hsr::mpr_penetration_inl).  Result -> s.mres.
-__device__ __noinline__ bool mpr(const Tab& t, Slice& s, const float* verts4, int g1, int g2, int gb0, double tol,
+// o: the slice of the environment the pair belongs to (poses, cached direction); s: the executing warp's slice (portal
+// scratch, result) - the same slice unless the warp serves another environment's job (phase-locked variant).
+__device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const float* verts4, int g1, int g2, int gb0, double tol,
                                  int max_iter, float* sep) {
   double* const out7 = s.mres;   // depth, direction, position (written by lane 0)
   const int lane = threadIdx.x & 31;
   enum { S_CACHE = 0, S_V1, S_V2, S_DISCOVER, S_REFINE, S_PENETRATE };
   const double eps = DBL_EPSILON;
-  V3d v0 = ld3(s.gpos + 3 * g1) - ld3(s.gpos + 3 * g2);
+  V3d v0 = ld3(o.gpos + 3 * g1) - ld3(o.gpos + 3 * g2);
   if (lane == 0) {
-    st3(s.portal + 3, ld3(s.gpos + 3 * g1)); st3(s.portal + 6, ld3(s.gpos + 3 * g2));
+    st3(s.portal + 3, ld3(o.gpos + 3 * g1)); st3(s.portal + 6, ld3(o.gpos + 3 * g2));
   }
   if (fabs(v0.x) < eps && fabs(v0.y) < eps && fabs(v0.z) < eps) v0.x += eps * 10;
   if (lane == 0) st3(s.portal, v0);
@@ -150,8 +163,8 @@ __device__ __noinline__ bool mpr(const Tab& t, Slice& s, const float* verts4, in
 #pragma unroll 1
   while (true) {
     // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along d
-    const V3d a1 = support(t, s, verts4, g1, gb0, d);
-    const V3d a2 = support(t, s, verts4, g2, gb0, -d);
+    const V3d a1 = support(t, o, verts4, g1, gb0, d);
+    const V3d a2 = support(t, o, verts4, g2, gb0, -d);
     const V3d v4 = a1 - a2;
     __syncwarp();
     if (lane == 0) { st3(s.portal + 36, v4); st3(s.portal + 39, a1); st3(s.portal + 42, a2); }
@@ -280,14 +293,20 @@ __device__ __noinline__ bool mpr(const Tab& t, Slice& s, const float* verts4, in
 }  // namespace wpe
 
 // ---------------------------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __grid_constant__ KArgs a, const __grid_constant__ PushInfo fi) {
+// LOCK = false: free-running warps (no block barrier after the table copy).
+// LOCK = true:  the same code with block barriers between the phases of a substep and around every pass of the solver loop,
+//               so that the 28 warps of the block run the same few-KB code region at the same time (instruction cache) while
+//               each still owns one environment; a phase then lasts as long as its slowest warp.
+template <bool LOCK>
+__global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const __grid_constant__ KArgs a, const __grid_constant__ PushInfo fi) {
   HSRB_DYN_SMEM(smem);
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const ModelT<float>& m = a.m;
   // ---- block-shared: model tables + hull vertices as float4 (one copy per block), after the warps' slices
   wpe::Tab& tw = *reinterpret_cast<wpe::Tab*>(smem + (size_t)wpb * sizeof(wpe::Slice));
-  float* const v4w = reinterpret_cast<float*>(smem + (size_t)wpb * sizeof(wpe::Slice) + sizeof(wpe::Tab));
+  wpe::Queue& Q = *reinterpret_cast<wpe::Queue*>(smem + (size_t)wpb * sizeof(wpe::Slice) + sizeof(wpe::Tab));
+  float* const v4w = reinterpret_cast<float*>(smem + (size_t)wpb * sizeof(wpe::Slice) + sizeof(wpe::Tab) + sizeof(wpe::Queue));
   {
     const int ng = m.ngeom, np = m.npair;
     for (int i = threadIdx.x; i < m.nvert * 4; i += blockDim.x) v4w[i] = fi.verts4[i];
@@ -295,7 +314,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
     TAB_COPY(gbase, fi.gbase, ng * 3) TAB_COPY(gmatw, fi.gmatw, ng * 9) TAB_COPY(pairc, fi.pairc, np * PUSH_PAIRC)
     TAB_COPY(ghalf, fi.ghalf, ng * 3) TAB_COPY(geom_rbound, m.geom_rbound, ng)
     TAB_COPY(geom_size, m.geom_size, ng * 3) TAB_COPY(pair_friction, m.pair_friction, np * 5)
-    TAB_COPY(geom_mat, m.geom_mat, ng * 9) TAB_COPY(geom_aabb, m.geom_aabb, ng * 3)
+    TAB_COPY(geom_aabb, m.geom_aabb, ng * 3)
+    {
+      int gb0_ = ng;
+      for (int i = ng - 1; i >= 0; i--) if (fi.gmove[i] == 2) gb0_ = i;
+      for (int i = threadIdx.x; i < (ng - gb0_) * 9 && i < WPE_MAXBG * 9; i += blockDim.x) tw.bgeom_mat[i] = m.geom_mat[9 * gb0_ + i];
+    }
     TAB_COPY(gmove, fi.gmove, ng) TAB_COPY(geom_type, m.geom_type, ng)
     TAB_COPY(geom_vertadr, m.geom_vertadr, ng) TAB_COPY(geom_vertnum, m.geom_vertnum, ng)
     TAB_COPY(pair_geom1, m.pair_geom1, np) TAB_COPY(pair_geom2, m.pair_geom2, np)
@@ -306,7 +330,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
       tw.pair_sr[k] = (float)(b2 == fi.robot_body) - (float)(b1 == fi.robot_body);
       tw.pair_sb[k] = (float)(b2 == fi.block_body) - (float)(b1 == fi.block_body);
     }
-    __syncthreads();   // the only block barrier of the kernel
+    if (threadIdx.x < 4) Q.cnt[threadIdx.x] = 0;
+    __syncthreads();   // the only block barrier of the free-running variant
   }
   const wpe::Tab& t = tw;
   const float* const verts4 = v4w;
@@ -323,9 +348,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
   const bool use_sep = !(a.opts & 1u);
 
 #pragma unroll 1
-  for (int env = blockIdx.x * wpb + wib; env < a.n; env += gridDim.x * wpb) {
+  for (int env0 = blockIdx.x * wpb; env0 < a.n; env0 += gridDim.x * wpb) {
+    const int env = env0 + wib;
+    const bool valid = env < a.n;
+    if (!LOCK && !valid) break;
     // ------------------------------------------------------------------ state -> shared memory
-    {
+    if (valid) {
       const float* st = a.state + (size_t)env * a.S;
       if (lane < 12) s.qpos[lane] = (lane < nq) ? st[lane] : 0.f;
       if (lane < 8) {
@@ -335,19 +363,26 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
       }
       if (lane < 3) s.mocap[lane] = st[nq + 2 * NV + lane];
       if (lane < 2) s.ctrl[lane] = (a.ctrl && lane < fi.act_n) ? a.ctrl[(size_t)env * m.nu + lane] : 0.f;
-      for (int i = lane; i < WI_COUNT; i += 32) s.wi[i] = 0;
+      if (lane < 4) s.wi[lane] = 0;
       for (int i = lane; i < 4 * m.npair; i += 32) s.sep[i] = 0.f;     // no cached separating directions
-      for (int i = lane; i < m.ngeom * 3; i += 32) { s.gpos[i] = t.gbase[i]; s.gaabb[i] = t.ghalf[i]; }
+      for (int i = lane; i < m.ngeom * 3; i += 32) s.gpos[i] = t.gbase[i];
       if (lane < 3) s.xb[lane] = 0;
       if (lane < 9) s.Rb[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
     }
     int n_iter = 0, n_ls = 0, sumcon = 0, sumefc = 0, kflop = 0, flags = 0, narrow_tot = 0;
     bool success = false;
     int taken = 0;
+    bool finished = !valid || a.nsub <= 0;
     __syncwarp();
 
 #pragma unroll 1
     for (int sb_ = 0; sb_ < a.nsub; sb_++) {
+      if (LOCK) { if (__syncthreads_and(finished)) break; }
+      else if (finished) break;
+      int nlimit = 0, ncon = 0, nefc = 0, narrow = 0, npflop = 0, ngrp = 0, nslot = 0, gdim = 0;
+      unsigned bits = 0;                // candidate pairs of this environment that passed the cull
+      int it = 0, ls_used = 0;
+      if (!finished) {
       // ---------------------------------------------------------------- poses (B.1), geometry in double
       if (HASB) {
         double qd[4] = {(double)s.qpos[5], (double)s.qpos[6], (double)s.qpos[7], (double)s.qpos[8]};
@@ -378,17 +413,16 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
             float Rbf[9], Rg[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) Rbf[k] = (float)Rb[k];
-            mulm(Rbf, t.geom_mat + 9 * gg, Rg);
+            mulm(Rbf, t.bgeom_mat + 9 * (gg - gb0), Rg);
             const float* h = t.geom_aabb + 3 * gg;
 #pragma unroll
             for (int i = 0; i < 3; i++)
-              s.gaabb[3 * gg + i] = fabsf(Rg[3 * i]) * h[0] + fabsf(Rg[3 * i + 1]) * h[1] + fabsf(Rg[3 * i + 2]) * h[2];
+              s.baabb[4 * (gg - gb0) + i] = fabsf(Rg[3 * i]) * h[0] + fabsf(Rg[3 * i + 1]) * h[1] + fabsf(Rg[3 * i + 2]) * h[2];
           }
         }
       }
       __syncwarp();
       // ---------------------------------------------------------------- active joint limits: groups 0 .. nlimit-1
-      int nlimit = 0;
       {
         bool act = false;
         float sg = 0.f, Dv = 0.f, ar = 0.f;
@@ -421,10 +455,10 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
         }
       }
       // ---------------------------------------------------------------- collision (B.3): contacts in pair order
-      int ncon = 0, nefc = nlimit, narrow = 0, npflop = 0;
-#pragma unroll 1
-      for (int base = 0; base < m.npair; base += 32) {
-        const int k = base + lane;
+      // cull: one candidate pair per lane (npair <= 32 for this kernel: WPE_MAXPAIR)
+      nefc = nlimit;
+      {
+        const int k = lane;
         bool hit = false;
         if (k < m.npair) {
           const int ga = t.pair_geom1[k], gb = t.pair_geom2[k];
@@ -435,16 +469,69 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
           } else {
             const float rr = t.geom_rbound[ga] + t.geom_rbound[gb];
             hit = dot(dp, dp) <= rr * rr;
-            const float* ha = s.gaabb + 3 * ga; const float* hb = s.gaabb + 3 * gb;
+            const float* ha = t.gmove[ga] == 2 ? s.baabb + 4 * (ga - gb0) : t.ghalf + 3 * ga;
+            const float* hb = t.gmove[gb] == 2 ? s.baabb + 4 * (gb - gb0) : t.ghalf + 3 * gb;
             hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
           }
         }
-        unsigned bits = __ballot_sync(FULL, hit);
+        bits = __ballot_sync(FULL, hit);
+      }
+      if (LOCK && lane == 0) {
+        // queue this environment's convex-convex candidates for the block's warps: a pair without a cached separating
+        // direction (in contact last time, or new) is a full refinement (~11 support evaluations) and goes to the front,
+        // a pair with one is usually a single support evaluation and goes to the back
+        unsigned bb = bits;
+        int kc = 0;
+        while (bb) {
+          const int pk = __ffs((int)bb) - 1;
+          bb &= bb - 1;
+          if (t.pair_func[pk] != NP_CONVEX_CONVEX) continue;
+          if (kc < WPE_ENVJOBS) {
+            const bool quick = use_sep && s.sep[4 * pk + 3] == 1.f;
+            const int code = (wib << 16) | (kc << 8) | pk;
+            if (quick) Q.jobs[WPE_MAXWARPS * WPE_ENVJOBS - 1 - atomicAdd(&Q.cnt[1], 1)] = code;
+            else Q.jobs[atomicAdd(&Q.cnt[0], 1)] = code;
+          }
+          kc++;
+        }
+      }
+      }
+      if (LOCK) {
+        __syncthreads();
+        // ---- every warp of the block (finished ones included) serves jobs: the owner's poses, this warp's portal scratch
+        const int nlong = Q.cnt[0], njobs = nlong + Q.cnt[1];
+#pragma unroll 1
+        while (true) {
+          int j = 0;
+          if (lane == 0) j = atomicAdd(&Q.cnt[2], 1);
+          j = __shfl_sync(FULL, j, 0);
+          if (j >= njobs) break;
+          const int code = j < nlong ? Q.jobs[j] : Q.jobs[WPE_MAXWARPS * WPE_ENVJOBS - 1 - (j - nlong)];
+          const int pk = code & 255;
+          wpe::Slice& o = *reinterpret_cast<wpe::Slice*>(smem + (size_t)(code >> 16) * sizeof(wpe::Slice));
+          const bool hitc = wpe::mpr(t, o, s, verts4, t.pair_geom1[pk], t.pair_geom2[pk], gb0, (double)m.mpr_tolerance, m.mpr_iterations,
+                                     use_sep ? o.sep + 4 * pk : nullptr);
+          if (lane == 0) {
+            float* r = o.jres + 14 * ((code >> 8) & 255);
+            r[0] = hitc ? 1.f : 0.f;
+            if (hitc) {
+              const double* r7 = s.mres;
+              r[1] = (float)(-r7[0]); r[2] = (float)r7[4]; r[3] = (float)r7[5]; r[4] = (float)r7[6];
+              make_frame(mk<double>(r7[1], r7[2], r7[3]), r + 5);
+            }
+          }
+          __syncwarp();
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) Q.cnt[threadIdx.x] = 0;   // empty again; the next jobs are queued after the solver's barriers
+      }
+      if (!finished) {
+      {
+        int kc = 0;
 #pragma unroll 1
         while (bits) {
-          const int l = __ffs((int)bits) - 1;
+          const int pk = __ffs((int)bits) - 1;
           bits &= bits - 1;
-          const int pk = base + l;
           const int func = t.pair_func[pk];
           const int ga = t.pair_geom1[pk], gb = t.pair_geom2[pk];
           const int dim = t.pair_condim[pk];
@@ -477,8 +564,23 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
             }
             if (nh > room) { nh = room; flags |= FLAG_CON_OVERFLOW; }
             ncon += nh; nefc += nh * dim;
+          } else if (func == NP_CONVEX_CONVEX && LOCK && kc < WPE_ENVJOBS) {
+            // the job's result record (written by the warp that served it)
+            const float* r = s.jres + 14 * kc;
+            kc++;
+            if (r[0] != 0.f) {
+              if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
+              else {
+                if (lane == 0) s.con_pair[ncon] = pk;
+                if (lane == 1) s.con_dist[ncon] = r[1];
+                if (lane >= 2 && lane < 5) s.con_pos[3 * ncon + lane - 2] = r[lane];
+                if (lane >= 5 && lane < 14) s.con_frame[9 * ncon + lane - 5] = r[lane];
+                ncon++; nefc += dim;
+              }
+            }
           } else if (func == NP_CONVEX_CONVEX || func == NP_PLANE_CONVEX) {
             bool hitc;
+            kc++;
             if (func == NP_PLANE_CONVEX) {
               const double* Ma = t.gmatw + 9 * ga;
               const wpe::V3d n = mk<double>(Ma[2], Ma[5], Ma[8]);
@@ -490,7 +592,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
               if (lane == 0) { double* r7 = s.mres; r7[0] = -dist; r7[1] = n.x; r7[2] = n.y; r7[3] = n.z; r7[4] = pos.x; r7[5] = pos.y; r7[6] = pos.z; }
               __syncwarp();
             } else {
-              hitc = wpe::mpr(t, s, verts4, ga, gb, gb0, (double)m.mpr_tolerance, m.mpr_iterations, use_sep ? s.sep + 4 * pk : nullptr);
+              hitc = wpe::mpr(t, s, s, verts4, ga, gb, gb0, (double)m.mpr_tolerance, m.mpr_iterations, use_sep ? s.sep + 4 * pk : nullptr);
             }
             if (hitc) {
               if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
@@ -506,7 +608,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
             }
           } else {   // box-box (block against the pan): hsr_core.h, rare
             WS<float> w;                                // view for hsr::box_box / add_contact
-            w.gpos = s.gpos; w.gaabb = s.gaabb; w.con_dist = s.con_dist; w.con_pos = s.con_pos; w.con_frame = s.con_frame;
+            w.gpos = s.gpos; w.gaabb = nullptr; w.con_dist = s.con_dist; w.con_pos = s.con_pos; w.con_frame = s.con_frame;
             w.con_pair = s.con_pair; w.con_adr = s.con_adr; w.wi = s.wi; w.sep = nullptr;
             const DevGrp<32> g;
             Geom<float> A, B;
@@ -527,8 +629,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
       }
       narrow_tot += narrow;
       __syncwarp();
-      const int ngrp = nlimit + ncon;
-      const int nslot = 6 * ngrp;
+      ngrp = nlimit + ncon;
+      nslot = 6 * ngrp;
       sumcon += ncon; sumefc += nefc;
 
       // ---------------------------------------------------------------- smooth forces (closed form, B.6): dof lanes
@@ -558,7 +660,6 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
         s.as[lane] = lane < NV ? q / fi.Mdiag[lane] : 0.f;
       }
       // ---------------------------------------------------------------- constraint rows: one contact per group lane (B.4/B.5)
-      int gdim = 0;
       if (lane < nlimit) gdim = 1;
       else if (lane < ngrp) {
         const int c = lane - nlimit;
@@ -629,11 +730,13 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
       // One loop whose body appears once in the instruction stream: [rows at the point] -> cost / forces / zones ->
       // bookkeeping of the phase -> Newton step.  Phases: 0 cost at qacc_smooth, 1 cost at qacc_warmstart (the usual
       // winner, evaluated last so that its rows and forces are in place), 2 back to qacc_smooth when it won, 3.. Newton.
-      int it = 0, ls_used = 0;
       if (ngrp == 0) {
         if (lane < 8) { s.x[lane] = s.as[lane]; s.qfc[lane] = 0.f; }
         __syncwarp();
-      } else {
+      }
+      }
+      {
+        bool solving = !finished && ngrp != 0;
         int zone = 0;
         float cN = 0.f, cT = 0.f;
         int phase = 0;
@@ -642,6 +745,9 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
         bool finishing = false;   // converged by the improvement test: stop after the next gradient (forces of the final point)
 #pragma unroll 1
         while (true) {
+          if (LOCK) { if (!__syncthreads_or(solving)) break; }
+          else if (!solving) break;
+          if (!solving) continue;
           if (phase < 3) {
             // jar = J x - aref (row slots across lanes)
             const push::F8 xv = push::ld8(xp);
@@ -731,7 +837,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
           gn = sqrtf(gn);
           if (finishing || (it > 0 && scale * gn < m.tolerance) || it >= m.iterations) {
             if (lane < 8) s.qfc[lane] = qf;
-            break;
+            solving = false;
+            continue;
           }
           // ---- Hessian J^T (cone Hessians) J as a sum of weighted outer products of Jacobian rows (see hsrb_push.cuh):
           //      quadratic-zone group: sum_r D_r J_r J_r^T;  cone-zone contact: Dm (p p^T + k q q^T) - Dm k sum_{a>=1} s_a^2 J_a J_a^T
@@ -846,7 +953,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
           __syncwarp();
           if (!(sn >= 1e-15f)) {
             if (lane < 8) s.qfc[lane] = qf;
-            break;
+            solving = false;
+            continue;
           }
           // ---- jv = J search (row slots across lanes)
           {
@@ -932,7 +1040,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
           }
           if (alpha == 0.f) {
             if (lane < 8) s.qfc[lane] = qf;
-            break;
+            solving = false;
+            continue;
           }
           if (lane < 8) s.x[lane] += alpha * s.srch[lane];
           for (int r = lane; r < nslot; r += 32) s.jar[r] += alpha * s.jv[r];
@@ -940,6 +1049,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
         }
         __syncwarp();
       }
+      if (LOCK) __syncthreads();
+      if (!finished) {
       n_iter += it; n_ls += ls_used;
       kflop += algorithmic_flops(m, false, ncon, nefc, it, ls_used, npflop);   // slides + free box: M is constant
 
@@ -987,10 +1098,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel(const __
         __syncwarp();
       }
       taken++;
-      if (reached) { success = true; break; }
+      if (reached) success = true;
+      if (reached || sb_ == a.nsub - 1) finished = true;
+      }
     }
     // ------------------------------------------------------------------ results: HBM once per action
-    {
+    if (valid) {
       __syncwarp();
       float* st = a.state + (size_t)env * a.S;
       const int nobs = nq + NV;

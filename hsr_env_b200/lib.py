@@ -36,6 +36,7 @@ SIGNATURES = {
     "hsrb_debug_substep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsrb_stats": (c_int, [c_void_p, POINTER(c_int64), c_void_p]),
     "hsrb_launch_info": (c_int, [c_void_p, POINTER(c_int)]),
+    "hsrb_measure_fp32_peak": (c_int, [c_int, POINTER(c_double)]),
     "hsrb_last_error": (c_char_p, []),
 }
 

@@ -117,6 +117,11 @@ int hsrb_stats(hsrb_t* h, int64_t* out16_host, void* stream);
  * path (1 general, 2 fast), threads per block. */
 int hsrb_launch_info(hsrb_t* h, int* out6_host);
 
+/* Measurement aid of bench.py (no reference counterpart): the device's FP32 FMA-loop peak in TFLOP/s (8 independent FMA
+ * chains per thread, 2 x 1024 threads per SM, best of 4 timed launches on the legacy stream; synchronises), the
+ * denominator of the FP32 roofline fraction SURVEY.md 8(d) defines. */
+int hsrb_measure_fp32_peak(int device, double* tflops_out_host);
+
 const char* hsrb_last_error(void);
 
 #ifdef __cplusplus

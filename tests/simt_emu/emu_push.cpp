@@ -50,21 +50,22 @@ extern "C" int emu_push_step(const void* blob, size_t bytes, int G, int threads,
   a.cfg.has_goal = has_goal; a.cfg.geofence = (float)geofence; a.cfg.qidx0 = 0; a.cfg.qidx1 = 2;
   a.n = n; a.S = S; a.nsub = nsub; a.mode = MODE_STEP;
   if (const char* o = getenv("HSRB_OPTS")) a.opts = (unsigned)strtoul(o, nullptr, 0);
-  a.ws_bytes = (unsigned)(G == 1 ? wpe::slice_bytes() : push::carve(a.m, nullptr, nullptr));
+  a.ws_bytes = (unsigned)(G <= 2 ? wpe::slice_bytes() : push::carve(a.m, nullptr, nullptr));
   a.state = state.data(); a.ctrl = c32.data(); a.obs = obs.data(); a.reward = reward.data(); a.done = done.data();
   a.success = succ.data(); a.taken = tk.data(); a.bad = bad.data(); a.stats = stats.data();
-  if (G == 1) {   // warp-per-environment kernel (hsrb_wpe.cuh): `threads` / 32 environments per block
+  if (G == 1 || G == 2) {   // warp-per-environment kernel (hsrb_wpe.cuh): `threads` / 32 environments per block; G = 2: phase-locked variant
     const int wpb = threads / 32;
     const int grid1 = (n + wpb - 1) / wpb;
     a.m.nefc_max = WPE_MAXROW;
-    emu::launch(grid1, threads, (size_t)a.ws_bytes * wpb + wpe::shared_tail(a.m), [&]() { hsrb_wpe_kernel(a, fi); });
+    if (G == 1) emu::launch(grid1, threads, (size_t)a.ws_bytes * wpb + wpe::shared_tail(a.m), [&]() { hsrb_wpe_kernel_t<false>(a, fi); });
+    else emu::launch(grid1, threads, (size_t)a.ws_bytes * wpb + wpe::shared_tail(a.m), [&]() { hsrb_wpe_kernel_t<true>(a, fi); });
   }
-  const int epb = G == 1 ? 1 : threads / G;
+  const int epb = G <= 2 ? 1 : threads / G;
   const int grid = (n + epb - 1) / epb;
   const size_t smem = (size_t)a.ws_bytes * epb + push::shared_tail(a.m);
   const int NV = m.nv;
 #define RUN(G_) { if (NV == 8) run<G_, 8>(a, fi, grid, threads, smem); else run<G_, 2>(a, fi, grid, threads, smem); }
-  if (G == 8) RUN(8) else if (G == 16) RUN(16) else if (G == 32) RUN(32) else if (G != 1) return -3;
+  if (G == 8) RUN(8) else if (G == 16) RUN(16) else if (G == 32) RUN(32) else if (G > 2) return -3;
 #undef RUN
   for (int e = 0; e < n; e++) {
     const float* st = state.data() + (size_t)e * S;

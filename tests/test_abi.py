@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def declared_symbols():
     text = (ROOT / "include" / "hsrb.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(hsrb_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(hsrb_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_exported_and_bound():
