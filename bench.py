@@ -398,7 +398,7 @@ def run_gpu(args):
     achieved_tf = r["flops"] / secs_max / 1e12 / world
     f_alg = r["flops"] / max(1.0, r["substeps"])
     value = world * n * args.steps / secs_max
-    kname = {"fast": "hsrb_push_kernel", "wpe": "hsrb_wpe_kernel"}.get(info["kernel"], "hsrb_step_kernel")
+    kname = {"fast": "hsrb_push_kernel", "wpe": "hsrb_wpe_kernel_t<true>"}.get(info["kernel"], "hsrb_step_kernel")
     line = {
         "metric": "env_actions_per_sec", "value": value, "unit": "env-actions/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs_max / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -177,15 +177,16 @@ int configure_fast(hsrb* h) {
 
 // the fast kernels test the env_wrapper-form goal only (one block against the goal point)
 bool use_fast(const hsrb* h) { return h->fast_ok && h->path != 1 && h->cfg.ngoal == 0; }
-// which of the two: path 3 = warp-per-environment kernel, 2 = lock-step kernel; 0 (auto) = the lock-step kernel unless
-// HSRB_FAST_KERNEL=wpe (measured on B200, round 2: 4096 envs 45.5 M substeps/s lock-step vs 40.6 M warp-per-environment,
-// 131072 envs 62.3 M vs 61.4 M)
+// which of the two: path 3 = warp-per-environment kernel (hsrb_wpe.cuh), 2 = 8-lane lock-step kernel (hsrb_push.cuh);
+// 0 (auto) = the warp-per-environment kernel, phase-locked, two teams per block - measured on B200, round 2, TimeLimit
+// workload: 48.4 M substeps/s at 4096 envs (lock-step 8-lane kernel 34.6 M, free-running warps 32.9 M), 65.8 M at
+// 131072 envs (52.3 M / 53.2 M); HSRB_FAST_KERNEL=push|wpe overrides (experiments)
 bool use_wpe(const hsrb* h) {
   if (!use_fast(h) || !h->wpe_ok) return false;
   if (h->path == 3) return true;
   if (h->path == 2) return false;
   const char* o = getenv("HSRB_FAST_KERNEL");
-  return o && o[0] == 'w';
+  return !(o && o[0] == 'p');
 }
 
 int configure_wpe(hsrb* h) {
@@ -226,8 +227,13 @@ int run(hsrb* h, KArgs& a, void* stream) {
     a.ws_bytes = h->wpe_ws;
     a.m.ncon_max = WPE_MAXCON; a.m.nefc_max = WPE_MAXROW;
     const size_t smem = (size_t)h->wpe_ws * (h->wpe_threads / 32) + wpe::shared_tail(h->dm);
-    const char* lk = getenv("HSRB_WPE_LOCK");   // phase-locked variant of the warp-per-environment kernel
-    CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream, lk && lk[0] == '1'));
+    // phase-locked variant with two teams per block by default; HSRB_WPE_LOCK=0: free-running warps, HSRB_WPE_TEAMS=1|2|4
+    const char* lk = getenv("HSRB_WPE_LOCK");
+    const char* tm = getenv("HSRB_WPE_TEAMS");
+    const bool lock = !(lk && lk[0] == '0');
+    const unsigned teams = tm ? (unsigned)atoi(tm) : 2u;
+    if (!(a.opts & 0xf0u)) a.opts |= (teams & 15u) << 4;
+    CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream, lock));
     h->launches++;
     return 0;
   }

@@ -53,7 +53,7 @@ struct alignas(16) Tab {   // block-shared model tables (one copy per block)
 };
 
 struct alignas(16) Slice {   // per-warp (= per-environment) slice
-  double xb[4], Rb[10], bmat[9 * WPE_MAXBG], gpos[WPE_MAXGEOM * 3], portal[46], mres[8];
+  double xb[4], Rb[10], bmat[9 * WPE_MAXBG], gpos[WPE_MAXGEOM * 3], portal[48], mres[8];   // portal: 5 vertices x 9 + the current direction
   float qpos[12], qvel[8], warm[8], mocap[4], ctrl[4];
   float baabb[4 * WPE_MAXBG];                                  // world AABB half extents of the block geoms (the others: Tab::ghalf)
   float qs[8], as[8], x[8], qfc[8], srch[8];
@@ -69,9 +69,10 @@ struct alignas(16) Slice {   // per-warp (= per-environment) slice
 // phase-locked variant: block-shared queue of the convex-convex narrowphase jobs of the block's environments; long jobs
 // (no cached separating direction: a full portal refinement) fill it from the front, quick ones from the back, the warps
 // pop from the front
+#define WPE_MAXTEAMS 4
 struct alignas(16) Queue {
-  int cnt[4];                                 // [0] long jobs, [1] quick jobs, [2] next to serve
-  int jobs[WPE_MAXWARPS * WPE_ENVJOBS];       // (owner warp << 16) | (slot << 8) | pair
+  int cnt[WPE_MAXTEAMS][4];                   // per team: [0] long jobs, [1] quick jobs, [2] next to serve
+  int jobs[WPE_MAXWARPS * WPE_ENVJOBS];       // (owner warp << 16) | (slot << 8) | pair; team k owns a contiguous share
 };
 
 __host__ __device__ inline size_t slice_bytes() { return sizeof(Slice); }
@@ -85,6 +86,25 @@ __host__ __device__ inline size_t shared_tail(const ModelT<float>& m) { return s
 namespace wpe {
 
 typedef V3<double> V3d;
+
+// Barriers of a TEAM of warps (phase-locked variant): the block's warps form 1, 2 or 4 teams that lock-step
+// independently of each other (named barriers 1 + team), so that while one team waits for its slowest member the others
+// keep the SM busy.  nthreads = warps of the team x 32.
+#if defined(HSRB_SIMT_EMU)
+__device__ __forceinline__ void team_sync(int team, int nthreads) { emu::named_barrier(1 + team, nthreads); }
+__device__ __forceinline__ bool team_and(int team, int nthreads, bool p) { return emu::named_vote(1 + team, nthreads, p, true); }
+#else
+__device__ __forceinline__ void team_sync(int team, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool team_and(int team, int nthreads, bool p) {
+  unsigned r;
+  asm volatile(
+      "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %3, 0;\n\tbar.red.and.pred r, %1, %2, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+      : "=r"(r) : "r"(1 + team), "r"(nthreads), "r"((unsigned)p) : "memory");
+  return r != 0;
+}
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -141,34 +161,47 @@ __device__ __forceinline__ void pcopy(Slice& s, int dst, int src) {
 __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const float* verts4, int g1, int g2, int gb0, double tol,
                                  int max_iter, float* sep) {
   double* const out7 = s.mres;   // depth, direction, position (written by lane 0)
+  double* const P = s.portal;    // P[9 k ..]: portal vertex k = v | v1 | v2 (k = 0 .. 4), P[45 .. 47]: the current direction
   const int lane = threadIdx.x & 31;
   enum { S_CACHE = 0, S_V1, S_V2, S_DISCOVER, S_REFINE, S_PENETRATE };
   const double eps = DBL_EPSILON;
-  V3d v0 = ld3(o.gpos + 3 * g1) - ld3(o.gpos + 3 * g2);
-  if (lane == 0) {
-    st3(s.portal + 3, ld3(o.gpos + 3 * g1)); st3(s.portal + 6, ld3(o.gpos + 3 * g2));
-  }
-  if (fabs(v0.x) < eps && fabs(v0.y) < eps && fabs(v0.z) < eps) v0.x += eps * 10;
-  if (lane == 0) st3(s.portal, v0);
-  __syncwarp();
   int state = S_V1;
-  V3d d;
-  if (sep && sep[3] == 1.f) {
-    state = S_CACHE;
-    d = normalized(mk<double>((double)sep[0], (double)sep[1], (double)sep[2]));
-  } else {
-    d = normalized(-v0);
+  {
+    V3d v0 = ld3(o.gpos + 3 * g1) - ld3(o.gpos + 3 * g2);
+    if (fabs(v0.x) < eps && fabs(v0.y) < eps && fabs(v0.z) < eps) v0.x += eps * 10;
+    V3d d;
+    if (sep && sep[3] == 1.f) {
+      state = S_CACHE;
+      d = normalized(mk<double>((double)sep[0], (double)sep[1], (double)sep[2]));
+    } else {
+      d = normalized(-v0);
+    }
+    __syncwarp();
+    if (lane == 0) { st3(P, v0); st3(P + 3, ld3(o.gpos + 3 * g1)); st3(P + 6, ld3(o.gpos + 3 * g2)); st3(P + 45, d); }
+    __syncwarp();
   }
   int guard = 0, it = 0;
+// publish the next direction and go round again
+#define WPE_NEXT_DIR() { __syncwarp(); if (lane == 0) st3(P + 45, d); __syncwarp(); continue; }
 #pragma unroll 1
   while (true) {
-    // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along d
-    const V3d a1 = support(t, o, verts4, g1, gb0, d);
-    const V3d a2 = support(t, o, verts4, g2, gb0, -d);
-    const V3d v4 = a1 - a2;
-    __syncwarp();
-    if (lane == 0) { st3(s.portal + 36, v4); st3(s.portal + 39, a1); st3(s.portal + 42, a2); }
-    __syncwarp();
+    // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along the direction in P[45..47].  Nothing
+    //      but a few integers stays in registers across the two calls: direction, v0 and the first support point go
+    //      through the warp's shared-memory scratch (the version that kept them live spilled ~1 KB per thread to local
+    //      memory, i.e. to L2 with this kernel's shared-memory carve-out, on the critical path of every iteration)
+    {
+      const V3d a1 = support(t, o, verts4, g1, gb0, ld3(P + 45));
+      if (lane == 0) st3(P + 39, a1);
+    }
+    {
+      const V3d a2 = support(t, o, verts4, g2, gb0, -ld3(P + 45));
+      __syncwarp();
+      if (lane == 0) { st3(P + 42, a2); st3(P + 36, ld3(P + 39) - a2); }
+      __syncwarp();
+    }
+    const V3d v4 = ld3(P + 36);
+    V3d d = ld3(P + 45);
+    const V3d v0 = ld3(P);
     double dt = dot(v4, d);
     bool enter_refine = false;
     if (state == S_CACHE) {
@@ -176,7 +209,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       if (lane == 0) sep[3] = 0.f;
       state = S_V1;
       d = normalized(-v0);
-      continue;
+      WPE_NEXT_DIR();
     }
     if (state <= S_DISCOVER) {
       if (is_zero(dt) || dt < 0) {                         // origin outside the support plane: disjoint (or touching)
@@ -190,7 +223,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       if (is_zero(dot(d, d))) {
         if (fabs(v4.x) < eps && fabs(v4.y) < eps && fabs(v4.z) < eps) return false;
         const double dep = norm(v4);
-        const V3d dir = v4 * (1.0 / dep), pos = (a1 + a2) * 0.5;
+        const V3d dir = v4 * (1.0 / dep), pos = (ld3(P + 39) + ld3(P + 42)) * 0.5;
         if (lane == 0) {
           out7[0] = dep; out7[1] = dir.x; out7[2] = dir.y; out7[3] = dir.z; out7[4] = pos.x; out7[5] = pos.y; out7[6] = pos.z;
           if (sep) sep[3] = 2.f;
@@ -200,7 +233,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       }
       d = normalized(d);
       state = S_V2;
-      continue;
+      WPE_NEXT_DIR();
     }
     if (state == S_V2) {
       pcopy(s, 2, 4);
@@ -211,7 +244,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
         d = -d;
       }
       state = S_DISCOVER; guard = 0;
-      continue;
+      WPE_NEXT_DIR();
     }
     if (state == S_DISCOVER) {
       pcopy(s, 3, 4);
@@ -227,7 +260,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       if (cont && guard < 64) {
         const V3d w1 = pv(s, 1), w2 = pv(s, 2);
         d = normalized(cross(w1 - v0, w2 - v0));
-        continue;
+        WPE_NEXT_DIR();
       }
       state = S_REFINE; guard = 0;
       enter_refine = true;
@@ -287,7 +320,9 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
         if (is_zero(dv) || dv > 0 || guard >= 256) state = S_PENETRATE;   // the portal encloses the origin ray
       }
     }
+    WPE_NEXT_DIR();
   }
+#undef WPE_NEXT_DIR
 }
 
 }  // namespace wpe
@@ -297,6 +332,16 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
 // LOCK = true:  the same code with block barriers between the phases of a substep and around every pass of the solver loop,
 //               so that the 28 warps of the block run the same few-KB code region at the same time (instruction cache) while
 //               each still owns one environment; a phase then lasts as long as its slowest warp.
+// per-phase cycle counters of the phase-locked variant (thread 0 of block 0, clock64 before and after each block barrier),
+// compiled in only with -DHSRB_PHASE_CLOCKS.  Slots (names of hsrb_stats): kinematics = poses + limits + cull + queueing,
+// mass_matrix = wait at the barrier before the job service, smooth = this warp's share of the job service, collision = wait
+// for the last job, rows = contact assembly + smooth forces + constraint rows + this warp's solver passes, solver = wait
+// for the slowest warp's solver, euler = goal test + integration
+#if defined(HSRB_PHASE_CLOCKS)
+#define WPE_PH(id) do { if (LOCK && threadIdx.x == 0) { const long long t_ = clock64(); ph[id] += (unsigned long long)(t_ - tlast) >> 4; tlast = t_; } } while (0)
+#else
+#define WPE_PH(id) do { } while (0)
+#endif
 template <bool LOCK>
 __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const __grid_constant__ KArgs a, const __grid_constant__ PushInfo fi) {
   HSRB_DYN_SMEM(smem);
@@ -330,7 +375,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       tw.pair_sr[k] = (float)(b2 == fi.robot_body) - (float)(b1 == fi.robot_body);
       tw.pair_sb[k] = (float)(b2 == fi.block_body) - (float)(b1 == fi.block_body);
     }
-    if (threadIdx.x < 4) Q.cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 4 * WPE_MAXTEAMS) (&Q.cnt[0][0])[threadIdx.x] = 0;
     __syncthreads();   // the only block barrier of the free-running variant
   }
   const wpe::Tab& t = tw;
@@ -346,6 +391,20 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
   for (int i = m.ngeom - 1; i >= 0; i--) if (t.gmove[i] == 2) gb0 = i;
   const float Mi = li < NV ? fi.Mdiag[li] : 1.0f, dampi = li < NV ? fi.damp[li] : 0.f;
   const bool use_sep = !(a.opts & 1u);
+  // teams of the phase-locked variant: opts bits 4..7 = number of teams (0 -> 1); the warps of a team are contiguous
+  int nteam = LOCK ? (int)((a.opts >> 4) & 15u) : 1;
+  if (nteam < 1 || nteam > WPE_MAXTEAMS || wpb % nteam != 0) nteam = 1;
+  const int wpt = wpb / nteam, team = wib / wpt, tthreads = 32 * wpt;
+  int* const qcnt = Q.cnt[team];
+  int* const qjobs = Q.jobs + team * wpt * WPE_ENVJOBS;
+  const int qcap = wpt * WPE_ENVJOBS;
+#if defined(WPE_DEBUG_JOBS)
+  long long dbg_long = 0, dbg_quick = 0; int dbg_nlong = 0, dbg_nquick = 0, dbg_hits = 0, dbg_jobs_total = 0, dbg_long_total = 0, dbg_sub = 0;
+#endif
+#if defined(HSRB_PHASE_CLOCKS)
+  unsigned long long ph[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#endif
 
 #pragma unroll 1
   for (int env0 = blockIdx.x * wpb; env0 < a.n; env0 += gridDim.x * wpb) {
@@ -377,8 +436,11 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
 
 #pragma unroll 1
     for (int sb_ = 0; sb_ < a.nsub; sb_++) {
-      if (LOCK) { if (__syncthreads_and(finished)) break; }
+      if (LOCK) { if (wpe::team_and(team, tthreads, finished)) break; }
       else if (finished) break;
+#if defined(HSRB_PHASE_CLOCKS)
+      if (LOCK && threadIdx.x == 0) tlast = clock64();
+#endif
       int nlimit = 0, ncon = 0, nefc = 0, narrow = 0, npflop = 0, ngrp = 0, nslot = 0, gdim = 0;
       unsigned bits = 0;                // candidate pairs of this environment that passed the cull
       int it = 0, ls_used = 0;
@@ -489,24 +551,29 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           if (kc < WPE_ENVJOBS) {
             const bool quick = use_sep && s.sep[4 * pk + 3] == 1.f;
             const int code = (wib << 16) | (kc << 8) | pk;
-            if (quick) Q.jobs[WPE_MAXWARPS * WPE_ENVJOBS - 1 - atomicAdd(&Q.cnt[1], 1)] = code;
-            else Q.jobs[atomicAdd(&Q.cnt[0], 1)] = code;
+            if (quick) qjobs[qcap - 1 - atomicAdd(&qcnt[1], 1)] = code;
+            else qjobs[atomicAdd(&qcnt[0], 1)] = code;
           }
           kc++;
         }
       }
       }
       if (LOCK) {
-        __syncthreads();
+        WPE_PH(PH_KIN);
+        wpe::team_sync(team, tthreads);
+        WPE_PH(PH_CRB);
         // ---- every warp of the block (finished ones included) serves jobs: the owner's poses, this warp's portal scratch
-        const int nlong = Q.cnt[0], njobs = nlong + Q.cnt[1];
+        const int nlong = qcnt[0], njobs = nlong + qcnt[1];
 #pragma unroll 1
         while (true) {
           int j = 0;
-          if (lane == 0) j = atomicAdd(&Q.cnt[2], 1);
+          if (lane == 0) j = atomicAdd(&qcnt[2], 1);
           j = __shfl_sync(FULL, j, 0);
           if (j >= njobs) break;
-          const int code = j < nlong ? Q.jobs[j] : Q.jobs[WPE_MAXWARPS * WPE_ENVJOBS - 1 - (j - nlong)];
+          const int code = j < nlong ? qjobs[j] : qjobs[qcap - 1 - (j - nlong)];
+#if defined(WPE_DEBUG_JOBS)
+          const long long tj0 = clock64();
+#endif
           const int pk = code & 255;
           wpe::Slice& o = *reinterpret_cast<wpe::Slice*>(smem + (size_t)(code >> 16) * sizeof(wpe::Slice));
           const bool hitc = wpe::mpr(t, o, s, verts4, t.pair_geom1[pk], t.pair_geom2[pk], gb0, (double)m.mpr_tolerance, m.mpr_iterations,
@@ -521,9 +588,17 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
             }
           }
           __syncwarp();
+#if defined(WPE_DEBUG_JOBS)
+          if (threadIdx.x == 0) { const long long dtj = clock64() - tj0; if (j < nlong) { dbg_long += dtj; dbg_nlong++; if (hitc) dbg_hits++; } else { dbg_quick += dtj; dbg_nquick++; } }
+#endif
         }
-        __syncthreads();
-        if (threadIdx.x < 3) Q.cnt[threadIdx.x] = 0;   // empty again; the next jobs are queued after the solver's barriers
+#if defined(WPE_DEBUG_JOBS)
+        if (threadIdx.x == 0) { dbg_jobs_total += njobs; dbg_long_total += nlong; dbg_sub++; }
+#endif
+        WPE_PH(PH_SMOOTH);
+        wpe::team_sync(team, tthreads);
+        WPE_PH(PH_COLLIDE);
+        if (wib == team * wpt && lane < 3) qcnt[lane] = 0;   // empty again; the next jobs are queued after the solver's barrier
       }
       if (!finished) {
       {
@@ -745,8 +820,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         bool finishing = false;   // converged by the improvement test: stop after the next gradient (forces of the final point)
 #pragma unroll 1
         while (true) {
-          if (LOCK) { if (!__syncthreads_or(solving)) break; }
+#if defined(WPE_PASS_LOCK)
+          if (LOCK) { if (!__syncthreads_or(solving)) break; }   // every solver pass in lock-step (measured: slower)
           else if (!solving) break;
+#else
+          if (!solving) break;   // the warps run their passes freely inside the solver phase (one barrier after the loop)
+#endif
           if (!solving) continue;
           if (phase < 3) {
             // jar = J x - aref (row slots across lanes)
@@ -1049,7 +1128,9 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         }
         __syncwarp();
       }
-      if (LOCK) __syncthreads();
+      WPE_PH(PH_ROWS);
+      if (LOCK) wpe::team_sync(team, tthreads);
+      WPE_PH(PH_SOLVE);
       if (!finished) {
       n_iter += it; n_ls += ls_used;
       kflop += algorithmic_flops(m, false, ncon, nefc, it, ls_used, npflop);   // slides + free box: M is constant
@@ -1101,6 +1182,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       if (reached) success = true;
       if (reached || sb_ == a.nsub - 1) finished = true;
       }
+      WPE_PH(PH_EULER);
     }
     // ------------------------------------------------------------------ results: HBM once per action
     if (valid) {
@@ -1130,5 +1212,15 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       __syncwarp();
     }
   }
+#if defined(HSRB_PHASE_CLOCKS)
+  if (LOCK && threadIdx.x == 0 && blockIdx.x == 0)
+    for (int k = 0; k < PH_COUNT; k++) atomicAdd(a.stats + ST_PHASE0 + k, ph[k]);
+#endif
+#if defined(WPE_DEBUG_JOBS)
+  if (LOCK && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    printf("block %d: substeps %d, jobs/substep %.1f (long %.1f); warp 0 served %d long jobs (%d hits) at %.0f cycles each, %d quick at %.0f cycles each\n",
+           blockIdx.x, dbg_sub, (double)dbg_jobs_total / dbg_sub, (double)dbg_long_total / dbg_sub, dbg_nlong, dbg_hits, dbg_nlong ? (double)dbg_long / dbg_nlong : 0.0,
+           dbg_nquick, dbg_nquick ? (double)dbg_quick / dbg_nquick : 0.0);
+#endif
 }
 #endif  // HSRB_WPE_IMPL

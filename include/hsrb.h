@@ -37,9 +37,10 @@ int hsrb_dims(hsrb_t* h, int* nq, int* nv, int* nu, int* nbody, int* nblock);
  * bad_state on either path. */
 int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max);
 
-/* Kernel selection: 0 = auto (the fast kernel (hsrb_push.cuh) when the model is a sliding base with at most
- * one free box - the README block-push family - else the general kernel), 1 = general kernel, 2 = fast kernel
- * (error if the model is outside that family).  Returns the path that will run (1 or 2). */
+/* Kernel selection: 0 = auto (for the sliding base with at most one free box - the README block-push family - the
+ * warp-per-environment kernel hsrb_wpe.cuh; else the general kernel), 1 = general kernel, 2 = the 8-lane lock-step
+ * kernel of the family (hsrb_push.cuh), 3 = the warp-per-environment kernel (2, 3: error if the model is outside the
+ * family).  Returns the path that will run (1, 2 or 3). */
 int hsrb_set_path(hsrb_t* h, int path);
 
 /* GoalSpec(a=block_space, b=goal_space, distance=geofence)  /root/reference/hsr/util.py:70-74, env.py:161-172

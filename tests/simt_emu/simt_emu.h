@@ -69,12 +69,35 @@ struct Block {
   std::vector<std::unique_ptr<Warp>> warps;
   std::unique_ptr<SpinBarrier> all;
   std::atomic<int> vote{0};
+  // named barriers (bar.sync id, nthreads): one barrier object + vote counter per id
+  std::mutex nmu;
+  std::map<int, std::unique_ptr<SpinBarrier>> named;
+  std::atomic<int> nvote[16];
+  SpinBarrier& nbar(int id, int n) {
+    std::lock_guard<std::mutex> l(nmu);
+    auto it = named.find(id);
+    if (it == named.end()) it = named.emplace(id, std::make_unique<SpinBarrier>(n)).first;
+    return *it->second;
+  }
 };
 
 inline thread_local Block* tl_block = nullptr;
 inline thread_local Warp* tl_warp = nullptr;
 inline thread_local int tl_lane = 0;
 inline unsigned char* dyn_smem = nullptr;
+
+inline void named_barrier(int id, int nthreads) { tl_block->nbar(id, nthreads).wait(); }
+// bar.red.and / .or over the threads of a named barrier
+inline bool named_vote(int id, int nthreads, bool p, bool is_and) {
+  Block& b = *tl_block;
+  SpinBarrier& bar = b.nbar(id, nthreads);
+  bar.wait();
+  b.nvote[id].store(0);
+  bar.wait();
+  if (is_and ? !p : p) b.nvote[id].fetch_add(1);
+  bar.wait();
+  return is_and ? b.nvote[id].load() == 0 : b.nvote[id].load() != 0;
+}
 
 }  // namespace emu
 

@@ -403,3 +403,30 @@ def test_control_loop_through_the_single_env_facade():
     assert env.in_range("block0", env.block_pos(), 1e-3) is True or env.in_range("block0", env.block_pos(), 1e-3) == True  # noqa: E712
     assert not env.in_range("block0", lambda: env.block_pos() + 1.0, .5)
     env.close()
+
+
+def test_wpe_kernel_variants_are_bitwise_identical(monkeypatch):
+    """The warp-per-environment kernel gives the same bits whether its warps run free or phase-locked in 1, 2 or 4 teams
+    (barriers and the shared narrowphase job queue change who computes what and when, not the arithmetic), over a whole
+    300-substep action of the bench workload."""
+    from hsr_env_b200.env import BatchedHSREnv
+    from hsr_env_b200.spaces import Box
+    from hsr_env_b200.util import GoalSpec
+    from scenarios import BLOCK_HI, BLOCK_LO, GOAL_HI, GOAL_LO
+
+    goals = [GoalSpec(Box(BLOCK_LO, BLOCK_HI), Box(GOAL_LO, GOAL_HI), .05)]
+    n = 4096
+    act = torch.rand(n, 2, generator=torch.Generator().manual_seed(2)) * 2 - 1
+    outs = []
+    for lock, teams in (("0", "1"), ("1", "1"), ("1", "2"), ("1", "4")):
+        monkeypatch.setenv("HSRB_WPE_LOCK", lock)
+        monkeypatch.setenv("HSRB_WPE_TEAMS", teams)
+        env = BatchedHSREnv("c2_push.hsrb", goals, n_envs=n, device="cuda:0", seed=4, kernel="wpe")
+        env.reset()
+        obs, reward, done, info = env.step(act)
+        outs.append((obs.cpu().numpy(), done.cpu().numpy(), info["substeps_taken"].cpu().numpy(), info["bad_state"].cpu().numpy()))
+        env.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    assert int(outs[0][3].sum()) == 0 and np.isfinite(outs[0][0]).all()
