@@ -303,6 +303,10 @@ def config_entry(r, n_total, steps, peak_tf, world, extra=None):
          "success_per_action": r["successes"] / (n_total * steps), "resets_per_action": r["resets"] / (n_total * steps),
          "kernel": r["info"]["kernel"], "lanes_per_env": r["info"]["lanes_per_env"], "threads_per_block": r["info"]["threads_per_block"],
          "grid": r["info"]["grid"], "smem_per_env": r["info"]["smem_per_env"], "resident_envs_per_sm": r["info"]["envs_per_sm"]}
+    ph = {k: r["stats1"]["phase_cycles"][k] - r["stats0"]["phase_cycles"][k] for k in r["stats1"]["phase_cycles"]}
+    if sum(ph.values()) > 0:   # only with the -DHSRB_PHASE_CLOCKS build (HSRB_LIB=.../libhsrb_prof.so)
+        tot = float(sum(ph.values()))
+        e["phase_share"] = {k: round(v / tot, 4) for k, v in ph.items()}
     if extra:
         e.update(extra)
     return e
@@ -442,7 +446,10 @@ def run_gpu(args):
     if not args.no_configs:
         cfgs = {}
         # configs[3]: 2^20 environments of the block-push model sharded over the ranks (strong scaling)
+        only = set(filter(None, args.only_configs.split(",")))
         n4 = args.c4_envs // world
+        if only and "c4" not in only:
+            n4 = 4096
         r4 = run_workload(torch, D, dev, blob=BLOB, goals=goals, starts=None, n_local=n4, env_offset=rank * n4,
                           steps=1, warmup=1, seed=args.seed + 1, kernel=args.kernel)
         cfgs["c4_1m_envs_sharded"] = config_entry(r4, n4 * world, 1, peak_tf, world, {
@@ -513,6 +520,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-configs", action="store_true", help="skip configs[2], [3], [4]")
+    ap.add_argument("--only-configs", default="", help="comma list of c3,c4,c5: run only these extra configs (experiments)")
     ap.add_argument("--c3-envs", type=int, default=16384)
     ap.add_argument("--c4-envs", type=int, default=1 << 20, help="total over all ranks")
     ap.add_argument("--c5-envs", type=int, default=4096)

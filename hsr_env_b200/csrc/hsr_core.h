@@ -79,6 +79,7 @@ enum { PH_KIN = 0, PH_CRB, PH_SMOOTH, PH_COLLIDE, PH_ROWS, PH_SOLVE, PH_EULER, P
 #define HSR_PHASE_START(w, g) do { } while (0)
 #endif
 #define HSR_LSQ 10
+#define HSR_MAXJOBS 16   // convex-convex narrowphase jobs an environment can queue per substep (phase-locked general kernel)
 
 // ------------------------------------------------------------------------------------------------ groups
 struct HostGrp {
@@ -89,6 +90,7 @@ struct HostGrp {
   HSR_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
   HSR_HD double max(double x) const { return x; }
   HSR_HD int min(int x) const { return x; }
+  template <typename T> HSR_HD T bcast(T x, int) const { return x; }
   HSR_HD void sync() const {}
 };
 
@@ -153,6 +155,7 @@ struct DevGrp {
     for (int o = G_ / 2; o > 0; o >>= 1) { const int t = __shfl_xor_sync(mask, x, o); x = t < x ? t : x; }
     return x;
   }
+  template <typename T> __device__ __forceinline__ T bcast(T x, int src) const { return __shfl_sync(mask, x, src, G_); }   // value of lane `src` of the group
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 #endif
@@ -222,15 +225,20 @@ struct WS {
   GT *xpos, *xquat, *xmat, *xipos, *anchor, *axis, *gpos, *com;
   T *qpos, *qvel, *warm, *ctrl, *mocap;
   T *cdof, *cinert, *binert;
+  T *cvel, *cacc, *cfrc;   // RNE scratch [nbody][6] each (shared memory on the device: local arrays would live in L2)
+  GT* trig;                // [njnt][2] cos, sin of the hinge joints' half angles (computed one joint per lane)
   T *M, *L, *H;
-  T *qfrc_smooth, *qacc_smooth, *qacc, *Ma, *grad, *search, *Mv, *tmpv;
+  T *qfrc_smooth, *qacc_smooth, *qacc, *Ma, *grad, *search, *Mv, *tmpv, *invd;
   T *gaabb;
   T *con_dist, *con_pos, *con_frame, *con_mu;
-  T *J, *W, *D, *aref, *jar, *jv, *force;
+  T *J, *D, *aref, *jar, *jv, *force;
+  T *wrow, *PQ, *wpq;   // Hessian as weighted outer products: row weights [ne], cone vectors p | q [nc][2][nv], their weights [nc][2]
   T *lsq;
   int *con_pair, *con_adr, *con_zone;
   int* wi;
   float* sep;   // [npair][4] cached separating direction + valid flag of each candidate pair (mpr_penetration's `sep`)
+  GT* jres;     // [HSR_MAXJOBS][8] phase-locked kernel: results of this environment's convex-convex jobs (hit, depth, dir, pos)
+  unsigned* cand;   // [8] phase-locked kernel: candidate pairs that passed the cull (bit mask, npair <= 256)
 };
 
 // Carve the workspace out of `base` (nullptr: just return the size in bytes).
@@ -243,17 +251,21 @@ HSR_HD size_t ws_carve(const ModelT<T>& m, WS<T>* w, unsigned char* base) {
   int nv = m.nv, nb = m.nbody, nc = m.ncon_max, ne = m.nefc_max;
   CARVE(xpos, GT, nb * 3) CARVE(xquat, GT, nb * 4) CARVE(xmat, GT, nb * 9) CARVE(xipos, GT, nb * 3)
   CARVE(anchor, GT, m.njnt * 3) CARVE(axis, GT, m.njnt * 3) CARVE(gpos, GT, m.ngeom * 3) CARVE(com, GT, nb * 3)
+  CARVE(trig, GT, m.njnt * 2)
   CARVE(qpos, T, m.nq) CARVE(qvel, T, nv) CARVE(warm, T, nv) CARVE(ctrl, T, m.nu > 0 ? m.nu : 1) CARVE(mocap, T, 3)
   CARVE(cdof, T, nv * 6) CARVE(cinert, T, nb * 10) CARVE(binert, T, nb * 10)
+  CARVE(cvel, T, nb * 6) CARVE(cacc, T, nb * 6) CARVE(cfrc, T, nb * 6)
   CARVE(M, T, nv * nv) CARVE(L, T, nv * nv) CARVE(H, T, nv * nv)
   CARVE(qfrc_smooth, T, nv) CARVE(qacc_smooth, T, nv) CARVE(qacc, T, nv) CARVE(Ma, T, nv) CARVE(grad, T, nv)
-  CARVE(search, T, nv) CARVE(Mv, T, nv) CARVE(tmpv, T, nv)
+  CARVE(search, T, nv) CARVE(Mv, T, nv) CARVE(tmpv, T, nv) CARVE(invd, T, nv)
   CARVE(gaabb, T, m.ngeom * 3)
   CARVE(con_dist, T, nc) CARVE(con_pos, T, nc * 3) CARVE(con_frame, T, nc * 9) CARVE(con_mu, T, nc)
-  CARVE(J, T, ne * nv) CARVE(W, T, ne * nv) CARVE(D, T, ne) CARVE(aref, T, ne) CARVE(jar, T, ne) CARVE(jv, T, ne)
+  CARVE(J, T, ne * nv) CARVE(wrow, T, ne) CARVE(PQ, T, 2 * nc * nv) CARVE(wpq, T, 2 * nc) CARVE(D, T, ne) CARVE(aref, T, ne) CARVE(jar, T, ne) CARVE(jv, T, ne)
   CARVE(force, T, ne) CARVE(lsq, T, nc * HSR_LSQ)
   CARVE(con_pair, int, nc) CARVE(con_adr, int, nc) CARVE(con_zone, int, nc) CARVE(wi, int, WI_COUNT)
   CARVE(sep, float, 4 * m.npair)
+  off += (8 - off % 8) % 8;
+  CARVE(jres, GT, 8 * HSR_MAXJOBS) CARVE(cand, unsigned, 8)
 #undef CARVE
   off += (16 - off % 16) % 16;
   return off;
@@ -267,6 +279,17 @@ template <typename T> HSR_HD void inert_mul(const T* I, const T* v, T* f) {  // 
   V3<T> fa = mk<T>(I[0] * w.x + I[3] * w.y + I[4] * w.z, I[3] * w.x + I[1] * w.y + I[5] * w.z,
                    I[4] * w.x + I[5] * w.y + I[2] * w.z) + cross(mc, vo);
   st3(f, fa); st3(f + 3, fl);
+}
+
+// cos / sin of the hinge joints' half angles, one joint per lane (the serial chain of kinematics_lane0 then only multiplies)
+template <typename T, typename Grp>
+HSR_HD void kinematics_trig(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  for (int j = g.lane; j < m.njnt; j += Grp::G) {
+    if (m.jnt_type[j] != JNT_HINGE) continue;
+    const GT h = ((GT)w.qpos[m.jnt_qposadr[j]] - (GT)m.qpos0[m.jnt_qposadr[j]]) * GT(0.5);
+    w.trig[2 * j] = cos(h); w.trig[2 * j + 1] = sin(h);
+  }
+  g.sync();
 }
 
 template <typename T>
@@ -302,8 +325,8 @@ HSR_HDC void kinematics_lane0(const ModelT<T>& m, WS<T>& w) {
         if (m.jnt_type[j] == JNT_SLIDE) {
           st3(pos, ld3(pos) + ax * q);
         } else {
-          GT h = q * GT(0.5), sn = sin(h);
-          GT dq[4] = {cos(h), sn * (GT)m.jnt_axis[3 * j], sn * (GT)m.jnt_axis[3 * j + 1], sn * (GT)m.jnt_axis[3 * j + 2]};
+          const GT sn = w.trig[2 * j + 1];
+          GT dq[4] = {w.trig[2 * j], sn * (GT)m.jnt_axis[3 * j], sn * (GT)m.jnt_axis[3 * j + 1], sn * (GT)m.jnt_axis[3 * j + 2]};
           quatmul(quat, dq, quat);
           quat2mat(quat, R);
           st3(pos, anc - mulv(R, ldg(m.jnt_pos + 3 * j)));
@@ -454,8 +477,36 @@ template <typename T> HSR_HDC void chol_solve(const T* L, int n, T* x) {
 // bit-identical to chol_factor's), then the rows below the diagonal are scaled.  The solves are column-oriented: once
 // x[i] is final the lanes subtract its column from the remaining entries.  With one lane (host port) this is the
 // serial algorithm.
-template <typename T, typename Grp> HSR_HD bool chol_factor_g(T* A, int n, const Grp& g) {
+template <typename T> HSR_HD T rsqrt_t(T x) {
+#if defined(__CUDA_ARCH__)
+  return (T)rsqrt(x);
+#else
+  return T(1) / sqrt(x);
+#endif
+}
+// `invd` (n entries) receives the reciprocals of the diagonal of L: the solves multiply instead of dividing.
+// n <= G (one row per lane: every kernel layout with nv <= lanes per environment, and the host port's G = 1 through
+// the other branch): lane i keeps its running element in a register, the pivot travels by a group broadcast instead of
+// through shared memory: one barrier per column instead of three, no division, no square root + division pair.
+template <typename T, typename Grp> HSR_HDC bool chol_factor_g(T* A, int n, T* invd, const Grp& g) {
   bool ok = true;
+  if (Grp::G > 1 && n <= Grp::G) {
+    const int i = g.lane;
+    for (int k = 0; k < n; k++) {
+      T s = 0;
+      if (i >= k && i < n) {
+        s = A[i * n + k];
+        for (int j = 0; j < k; j++) s -= A[i * n + j] * A[k * n + j];
+      }
+      T d = g.bcast(s, k);
+      if (!(d > Lim<T>::minval())) { d = Lim<T>::minval(); ok = false; }
+      const T rs = rsqrt_t(d);
+      if (i >= k && i < n) A[i * n + k] = (i == k) ? d * rs : s * rs;
+      if (i == k) invd[k] = rs;
+      g.sync();
+    }
+    return ok;
+  }
   for (int k = 0; k < n; k++) {
     for (int i = k + g.lane; i < n; i += Grp::G) {
       T s = A[i * n + k];
@@ -465,24 +516,42 @@ template <typename T, typename Grp> HSR_HD bool chol_factor_g(T* A, int n, const
     g.sync();
     T d = A[k * n + k];
     if (!(d > Lim<T>::minval())) { d = Lim<T>::minval(); ok = false; }
-    d = sqrt(d);
-    const T inv = T(1) / d;
+    const T rs = rsqrt_t(d);
     g.sync();   // every lane has read the pivot
-    for (int i = k + g.lane; i < n; i += Grp::G) A[i * n + k] = (i == k) ? d : A[i * n + k] * inv;
+    for (int i = k + g.lane; i < n; i += Grp::G) A[i * n + k] = (i == k) ? d * rs : A[i * n + k] * rs;
+    if (g.lane == 0) invd[k] = rs;
     g.sync();
   }
   return ok;
 }
-template <typename T, typename Grp> HSR_HD void chol_solve_g(const T* L, int n, T* x, const Grp& g) {
+template <typename T, typename Grp> HSR_HDC void chol_solve_g(const T* L, int n, const T* invd, T* x, const Grp& g) {
+  if (Grp::G > 1 && n <= Grp::G) {
+    // lane r keeps x[r] in a register; the finished component travels by a group broadcast
+    const int r = g.lane;
+    T xr = r < n ? x[r] : T(0);
+    for (int i = 0; i < n; i++) {        // L y = b
+      const T xi = g.bcast(xr, i) * invd[i];
+      if (r == i) xr = xi;
+      else if (r > i && r < n) xr -= L[r * n + i] * xi;
+    }
+    for (int i = n - 1; i >= 0; i--) {   // L^T x = y
+      const T xi = g.bcast(xr, i) * invd[i];
+      if (r == i) xr = xi;
+      else if (r < i) xr -= L[i * n + r] * xi;
+    }
+    if (r < n) x[r] = xr;
+    g.sync();
+    return;
+  }
   for (int i = 0; i < n; i++) {        // L y = b
-    const T xi = x[i] / L[i * n + i];
+    const T xi = x[i] * invd[i];
     g.sync();
     if (g.lane == 0) x[i] = xi;
     for (int r = i + 1 + g.lane; r < n; r += Grp::G) x[r] -= L[r * n + i] * xi;
     g.sync();
   }
   for (int i = n - 1; i >= 0; i--) {   // L^T x = y
-    const T xi = x[i] / L[i * n + i];
+    const T xi = x[i] * invd[i];
     g.sync();
     if (g.lane == 0) x[i] = xi;
     for (int r = g.lane; r < i; r += Grp::G) x[r] -= L[i * n + r] * xi;
@@ -504,7 +573,9 @@ template <typename T> HSR_HD void cross_force(const T* v, const T* f, T* r) {
 template <typename T>
 HSR_HDC void smooth_lane0(const ModelT<T>& m, WS<T>& w) {
   int nv = m.nv;
-  T cvel[HSRB_MAXBODY][6], cacc[HSRB_MAXBODY][6], cfrc[HSRB_MAXBODY][6];
+  T (*cvel)[6] = reinterpret_cast<T(*)[6]>(w.cvel);
+  T (*cacc)[6] = reinterpret_cast<T(*)[6]>(w.cacc);
+  T (*cfrc)[6] = reinterpret_cast<T(*)[6]>(w.cfrc);
   for (int k = 0; k < 6; k++) { cvel[0][k] = 0; cacc[0][k] = 0; cfrc[0][k] = 0; }
   cacc[0][3] = -m.gravity[0]; cacc[0][4] = -m.gravity[1]; cacc[0][5] = -m.gravity[2];
   for (int b = 1; b < m.nbody; b++) {
@@ -557,8 +628,8 @@ HSR_HD void smooth_solve(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   for (int k = g.lane; k < nv * nv; k += Grp::G) w.L[k] = w.M[k];
   for (int i = g.lane; i < nv; i += Grp::G) w.qacc_smooth[i] = w.qfrc_smooth[i];
   g.sync();
-  if (!chol_factor_g(w.L, nv, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
-  chol_solve_g(w.L, nv, w.qacc_smooth, g);
+  if (!chol_factor_g(w.L, nv, w.invd, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
+  chol_solve_g(w.L, nv, w.invd, w.qacc_smooth, g);
 }
 
 // ------------------------------------------------------------------------------------------------ B.3 collision
@@ -1066,6 +1137,64 @@ HSR_HDC int collision(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
   return ncon;
 }
 
+// The same collision stage in two halves for the phase-locked kernel (hsrb_step_lock_kernel, 32 lanes per environment):
+// the cull leaves a bit mask of the candidate pairs in w.cand; between the halves the convex-convex candidates are
+// refined by ANY warp of the block (block-shared job queue) into w.jres; the second half appends the contacts in pair
+// order exactly as collision() does, taking the queued pairs' results from w.jres.
+template <typename T, typename Grp>
+HSR_HD void collision_cull(const ModelT<T>& m, WS<T>& w, const Grp& g) {
+  static_assert(Grp::G == 32 || Grp::G == 1, "one ballot = 32 candidate pairs");
+  for (int base = 0; base < m.npair; base += 32) {
+    unsigned bits = 0;
+    for (int k0 = 0; k0 < 32; k0 += Grp::G) {
+      int k = base + k0 + g.lane;
+      bool hit = false;
+      if (k < m.npair) {
+        int a = m.pair_geom1[k], b = m.pair_geom2[k];
+        V3<T> dp = cvt<T>(ld3(w.gpos + 3 * b) - ld3(w.gpos + 3 * a));
+        if (m.geom_type[a] == GEOM_PLANE) {
+          Geom<T> P;
+          load_geom(m, w, a, P);
+          hit = dot(dp, cvt<T>(mcol(P.mat, 2))) <= m.geom_rbound[b];
+        } else {
+          T rr = m.geom_rbound[a] + m.geom_rbound[b];
+          hit = dot(dp, dp) <= rr * rr;
+          const T* ha = w.gaabb + 3 * a; const T* hb = w.gaabb + 3 * b;
+          hit = hit && fabs(dp.x) <= ha[0] + hb[0] && fabs(dp.y) <= ha[1] + hb[1] && fabs(dp.z) <= ha[2] + hb[2];
+        }
+      }
+      bits |= g.ballot(hit) << k0;
+    }
+    if (g.lane == 0) w.cand[base >> 5] = bits;
+  }
+  g.sync();
+}
+template <typename T, typename Grp>
+HSR_HD int collision_assemble(const ModelT<T>& m, WS<T>& w, const Grp& g, int& nrow) {
+  int ncon = 0, narrow = 0, npflop = 0, kc = 0;
+  for (int base = 0; base < m.npair; base += 32) {
+    unsigned bits = w.cand[base >> 5];
+    while (bits) {
+      int l = 0;
+      while (!((bits >> l) & 1u)) l++;
+      bits &= bits - 1;
+      const int pk = base + l;
+      narrow++;
+      if (m.pair_func[pk] == NP_CONVEX_CONVEX && kc < HSR_MAXJOBS) {
+        const GT* r = w.jres + 8 * kc;
+        kc++;
+        npflop += 5000;
+        if (r[0] != 0) add_contact(m, w, g, ncon, nrow, pk, -r[1], mk<GT>(r[5], r[6], r[7]), mk<GT>(r[2], r[3], r[4]));
+      } else {
+        if (m.pair_func[pk] == NP_CONVEX_CONVEX) kc++;
+        narrow_pair(m, w, g, pk, ncon, nrow, npflop);
+      }
+    }
+  }
+  if (g.lane == 0) { w.wi[WI_NARROW] += narrow; w.wi[WI_NPFLOP] = npflop; }
+  return ncon;
+}
+
 // ------------------------------------------------------------------------------------------------ B.4 / B.5
 // Row parameters are evaluated in double and rounded once: R = (1 - imp)/imp * diag cancels three digits of imp.
 template <typename T> HSR_HD GT impedance(const T* solimp, GT pos) {
@@ -1174,7 +1303,12 @@ HSR_HD int cone_zone(const T* x, int dim, T mu, const T* fri, T& N, T& Tn) {
   return 2;
 }
 
-// constraint cost of the current w.jar (rows across lanes / one contact per lane); optionally force + W rows
+// constraint cost of the current w.jar (rows across lanes / one contact per lane).  full: also the forces and the pieces
+// of the Hessian J^T (cone Hessians) J as a sum of weighted outer products of Jacobian rows (no ne x nv matrix W):
+//   quadratic zone / active limit:  sum_r D_r J_r J_r^T                                            -> w.wrow
+//   cone zone (U_a = jar_a s_a, u = U / T, s_0 = mu, s_a = fri_a-1, k = mu (N - mu T) / T):
+//       Dm (p p^T + k q q^T) - Dm k sum_{a>=1} s_a^2 J_a J_a^T,  p = mu J_0 - mu sum_{a>=1} u_a s_a J_a,  q = sum_{a>=1} u_a s_a J_a
+//   i.e. the 6x6 cone block Dm S (v v^T - k (I_t - u u^T)) S of the row formulation, v = e_0 - mu u, never formed.
 template <typename T, typename Grp>
 HSR_HDC T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, bool full) {
   int nv = m.nv;
@@ -1185,8 +1319,7 @@ HSR_HDC T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlim
     if (act) cost += T(0.5) * w.D[i] * x * x;
     if (full) {
       w.force[i] = act ? -w.D[i] * x : T(0);
-      T s = act ? w.D[i] : T(0);
-      for (int d = 0; d < nv; d++) w.W[i * nv + d] = s * w.J[i * nv + d];
+      w.wrow[i] = act ? w.D[i] : T(0);
     }
   }
   for (int c = g.lane; c < ncon; c += Grp::G) {
@@ -1199,14 +1332,14 @@ HSR_HDC T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlim
     int zone;
     if (dim == 1) { zone = x[0] < 0 ? 1 : 0; N = x[0]; Tn = 0; }
     else zone = cone_zone(x, dim, mu, fri, N, Tn);
-    if (full) w.con_zone[c] = zone;
+    if (full) { w.con_zone[c] = zone; w.wpq[2 * c] = 0; w.wpq[2 * c + 1] = 0; }
     if (zone == 0) {
-      if (full) for (int r = 0; r < dim; r++) { w.force[r0 + r] = 0; for (int d = 0; d < nv; d++) w.W[(r0 + r) * nv + d] = 0; }
+      if (full) for (int r = 0; r < dim; r++) { w.force[r0 + r] = 0; w.wrow[r0 + r] = 0; }
     } else if (zone == 1) {
       for (int r = 0; r < dim; r++) {
         T D = w.D[r0 + r];
         cost += T(0.5) * D * x[r] * x[r];
-        if (full) { w.force[r0 + r] = -D * x[r]; for (int d = 0; d < nv; d++) w.W[(r0 + r) * nv + d] = D * w.J[(r0 + r) * nv + d]; }
+        if (full) { w.force[r0 + r] = -D * x[r]; w.wrow[r0 + r] = D; }
       }
     } else {
       T Dm = w.D[r0] / (mu * mu * (1 + mu * mu));
@@ -1215,28 +1348,26 @@ HSR_HDC T constraint_update(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlim
       if (full) {
         T f0 = -Dm * NT * mu;
         w.force[r0] = f0;
-        T U[6], scl[6];
-        scl[0] = mu; U[0] = N;
-        for (int j = 1; j < dim; j++) { scl[j] = fri[j - 1]; U[j] = x[j] * fri[j - 1]; w.force[r0 + j] = -f0 / Tn * U[j] * fri[j - 1]; }
-        // cone Hessian (in jar space) times the contact Jacobian rows -> W rows
         T invT = T(1) / Tn;
-        T Hc[36];
-        for (int a = 0; a < dim; a++) for (int b = 0; b < dim; b++) {
-          T h;
-          if (a == 0 && b == 0) h = 1;
-          else if (a == 0) h = -mu * U[b] * invT;
-          else if (b == 0) h = -mu * U[a] * invT;
-          else {
-            T uu = U[a] * U[b] * invT * invT;
-            h = mu * mu * uu - mu * NT * ((a == b ? invT : T(0)) - uu * invT);
-          }
-          Hc[a * 6 + b] = Dm * scl[a] * h * scl[b];
+        T kap = mu * NT * invT;
+        T cq[6];
+        w.wrow[r0] = 0;
+        for (int j = 1; j < dim; j++) {
+          T sa = fri[j - 1];
+          T U = x[j] * sa;
+          w.force[r0 + j] = -f0 * invT * U * sa;
+          cq[j] = U * invT * sa;
+          w.wrow[r0 + j] = -Dm * kap * sa * sa;
         }
-        for (int a = 0; a < dim; a++) for (int d = 0; d < nv; d++) {
-          T s = 0;
-          for (int b = 0; b < dim; b++) s += Hc[a * 6 + b] * w.J[(r0 + b) * nv + d];
-          w.W[(r0 + a) * nv + d] = s;
+        T* P = w.PQ + (size_t)2 * c * nv;
+        T* Qv = P + nv;
+        for (int d = 0; d < nv; d++) {
+          T q = 0;
+          for (int j = 1; j < dim; j++) q += cq[j] * w.J[(r0 + j) * nv + d];
+          Qv[d] = q;
+          P[d] = mu * w.J[r0 * nv + d] - mu * q;
         }
+        w.wpq[2 * c] = Dm; w.wpq[2 * c + 1] = Dm * kap;
       }
     }
   }
@@ -1400,13 +1531,23 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
       while (rem > a) { rem -= a + 1; a++; }
       int b = rem;  // a >= b
       T s = w.M[a * nv + b];
-      for (int r = 0; r < nefc; r++) s += w.J[r * nv + a] * w.W[r * nv + b];
+      for (int r = 0; r < nefc; r++) {
+        const T wr = w.wrow[r];
+        if (wr != 0) s += wr * w.J[r * nv + a] * w.J[r * nv + b];
+      }
+      for (int c = 0; c < ncon; c++) {
+        const T wp = w.wpq[2 * c];
+        if (wp != 0) {
+          const T* P = w.PQ + (size_t)2 * c * nv;
+          s += wp * P[a] * P[b] + w.wpq[2 * c + 1] * P[nv + a] * P[nv + b];
+        }
+      }
       w.H[a * nv + b] = s;
     }
     for (int i = g.lane; i < nv; i += Grp::G) w.search[i] = -w.grad[i];
     g.sync();
-    if (!chol_factor_g(w.H, nv, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
-    chol_solve_g(w.H, nv, w.search, g);
+    if (!chol_factor_g(w.H, nv, w.invd, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
+    chol_solve_g(w.H, nv, w.invd, w.search, g);
     T sn = 0, dec = 0;
     for (int i = g.lane; i < nv; i += Grp::G) { sn += w.search[i] * w.search[i]; dec -= w.grad[i] * w.search[i]; }
     sn = sqrt(g.sum(sn));
@@ -1465,8 +1606,8 @@ HSR_HD void euler_solve(const ModelT<T>& m, WS<T>& w, const Grp& g) {
     for (int k = g.lane; k < nv * nv; k += Grp::G) { const int i = k / nv; w.H[k] = w.M[k] + ((k - i * nv == i) ? dt * m.dof_damping[i] : T(0)); }
     for (int i = g.lane; i < nv; i += Grp::G) x[i] = w.qfrc_smooth[i] + w.tmpv[i];
     g.sync();
-    if (!chol_factor_g(w.H, nv, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
-    chol_solve_g(w.H, nv, x, g);
+    if (!chol_factor_g(w.H, nv, w.invd, g) && g.lane == 0) w.wi[WI_FLAGS] |= FLAG_CHOL;
+    chol_solve_g(w.H, nv, w.invd, x, g);
   } else {
     for (int i = g.lane; i < nv; i += Grp::G) x[i] = w.qacc[i];
     g.sync();
@@ -1540,6 +1681,7 @@ HSR_HDC int algorithmic_flops(const ModelT<T>& m, int nc, int ne, int it, int ls
 template <typename T, typename Grp>
 HSR_HDC void forward(const ModelT<T>& m, WS<T>& w, const Grp& g) {
   HSR_PHASE_START(w, g);
+  kinematics_trig(m, w, g);
   if (g.lane == 0) kinematics_lane0(m, w);
   g.sync();
   HSR_PHASE(w, g, PH_KIN);

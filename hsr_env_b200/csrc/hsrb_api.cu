@@ -74,6 +74,9 @@ struct hsrb {
   int fast_lanes = 8, fast_threads = 0, fast_grid = 0, fast_bps = 0;
   unsigned fast_ws = 0;
   char fast_why[128] = "";
+  // phase-locked general kernel (hsrb_step_lock_kernel): STEP launches of the general path
+  bool lock_configured = false;
+  int lock_threads = 0, lock_grid = 0, lock_bps = 0;
   // warp-per-environment kernel of the same family (hsrb_wpe.cuh)
   bool wpe_ok = false, wpe_configured = false;
   int wpe_threads = 0, wpe_grid = 0, wpe_bps = 0;
@@ -211,6 +214,33 @@ int configure_wpe(hsrb* h) {
   return 0;
 }
 
+// STEP launches of the general path: one warp per environment, as many warps per block as shared memory holds
+int configure_lock(hsrb* h) {
+  if (h->lock_configured) return 0;
+  h->ws_bytes = (unsigned)ws_carve<float>(h->dm, nullptr, nullptr);
+  const size_t tail = lock_tail_bytes();
+  int wpb = (int)((227 * 1024 - tail) / h->ws_bytes);
+  if (wpb < 1) return fail(-3, "no launch configuration fits: workspace %u bytes per environment", h->ws_bytes);
+  if (wpb > HSRB_LOCK_MAXWARPS) wpb = HSRB_LOCK_MAXWARPS;
+  const int need_w = (h->n + h->num_sm - 1) / h->num_sm;
+  if (wpb > need_w) wpb = need_w;
+  if (const char* o = getenv("HSRB_LOCK_WPB")) { int v = atoi(o); if (v >= 1 && v <= wpb) wpb = v; }   // experiments
+  h->lock_threads = 32 * wpb;
+  const size_t smem = (size_t)h->ws_bytes * wpb + tail;
+  CU(hsrb_prepare_step_lock(smem, h->lock_threads, &h->lock_bps));
+  if (h->lock_bps < 1) return fail(-3, "phase-locked general kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+  const int need = (h->n + wpb - 1) / wpb;
+  const int cap = h->lock_bps * h->num_sm;
+  h->lock_grid = need < cap ? need : cap;
+  h->lock_configured = true;
+  return 0;
+}
+bool use_lock(const hsrb* h) {
+  if (h->hm.m.npair > 256) return false;
+  const char* o = getenv("HSRB_GENERAL_LOCK");
+  return !(o && o[0] == '0');
+}
+
 KArgs base_args(hsrb* h) {
   KArgs a;
   memset(&a, 0, sizeof(a));
@@ -248,6 +278,16 @@ int run(hsrb* h, KArgs& a, void* stream) {
     return 0;
   }
   if (a.mode == MODE_STEP && h->path == 2) return fail(-3, "fast path not available for this model: %s", h->fast_why);
+  if (a.mode == MODE_STEP && use_lock(h) && !h->lanes_req) {
+    int rc = configure_lock(h);
+    if (rc) return rc;
+    a.ws_bytes = h->ws_bytes;
+    a.m.ncon_max = h->dm.ncon_max; a.m.nefc_max = h->dm.nefc_max;
+    const size_t smem = (size_t)h->ws_bytes * (h->lock_threads / 32) + lock_tail_bytes();
+    CU(hsrb_launch_step_lock(a, h->lock_grid, h->lock_threads, smem, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+  }
   int rc = configure(h);
   if (rc) return rc;
   a.ws_bytes = h->ws_bytes;
@@ -396,6 +436,7 @@ int hsrb_config(hsrb_t* h, int lanes_per_env, int ncon_max, int nefc_max) {
   h->configured = false;
   h->fast_configured = false;
   h->wpe_configured = false;
+  h->lock_configured = false;
   CU(cudaSetDevice(h->device));
   return configure(h);
 }
@@ -623,6 +664,13 @@ int hsrb_launch_info(hsrb_t* h, int* out4) {  // out4: 6 ints
     if (rc) return rc;
     out4[0] = h->fast_lanes; out4[1] = (int)h->fast_ws; out4[2] = h->fast_bps * (h->fast_threads / h->fast_lanes); out4[3] = h->fast_grid;
     out4[4] = 2; out4[5] = h->fast_threads;
+    return 0;
+  }
+  if (use_lock(h) && !h->lanes_req) {
+    rc = configure_lock(h);
+    if (rc) return rc;
+    out4[0] = 32; out4[1] = (int)h->ws_bytes; out4[2] = h->lock_bps * (h->lock_threads / 32); out4[3] = h->lock_grid;
+    out4[4] = 1; out4[5] = h->lock_threads;
     return 0;
   }
   out4[0] = h->lanes; out4[1] = (int)h->ws_bytes; out4[2] = h->blocks_per_sm * (32 / h->lanes); out4[3] = h->grid;

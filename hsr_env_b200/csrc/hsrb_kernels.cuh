@@ -92,11 +92,14 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
           unsigned ep = a.episode[env];
           a.episode[env] = ep + 1;
           reset_lane0(a.m, a.cfg, w, a.seed, (uint32_t)(a.env_off + (unsigned long long)env), ep);
-          kinematics_lane0(a.m, w);  // sim.forward(): normalises free-joint quaternions in qpos
         }
+        g.sync();
+        kinematics_trig(a.m, w, g);
+        if (g.lane == 0) kinematics_lane0(a.m, w);  // sim.forward(): normalises free-joint quaternions in qpos
         g.sync();
       }
     } else {  // MODE_FORWARD: body positions of the current state (data.get_body_xpos, env.py:144,180,184)
+      kinematics_trig(a.m, w, g);
       if (g.lane == 0) kinematics_lane0(a.m, w);
       g.sync();
       if (a.body_xpos)
@@ -139,6 +142,175 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
     g.sync();
   }
 }
+
+// ------------------------------------------------------------------------------------------------ phase-locked general kernel
+// The action kernel of the general path for STEP launches: one WARP per environment (32 lanes), a block of several warps
+// that run the phases of a substep together (team barriers: the warps share the instruction cache instead of thrashing it)
+// and share ONE queue of convex-convex narrowphase jobs: any warp refines any environment's candidate pair (the owner's
+// poses, the serving warp's registers), so an environment with ten hull pairs near contact (the gripper on the pan,
+// configs[2]) no longer refines them one after the other.  Same arithmetic as hsrb_step_kernel<32>: the stages are the
+// functions of hsr_core.h, bitwise.
+#define HSRB_LOCK_MAXWARPS 12
+struct LockQueue {
+  int cnt[4];                                    // [0] long jobs, [1] quick jobs, [2] next to serve
+  int jobs[HSRB_LOCK_MAXWARPS * HSR_MAXJOBS];    // (owner warp << 16) | (slot << 8) | pair
+};
+__host__ __device__ inline size_t lock_tail_bytes() { return sizeof(LockQueue) + 16; }
+
+#if defined(HSRB_STEP_LOCK_IMPL)   // defined by the translation unit that owns the kernel (hsrb_step_lock.cu, the emulated build)
+__global__ void __launch_bounds__(32 * HSRB_LOCK_MAXWARPS) hsrb_step_lock_kernel(const __grid_constant__ KArgs a) {
+  HSRB_DYN_SMEM(smem);
+  typedef DevGrp<32> Grp;
+  const Grp g;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const ModelT<float>& m = a.m;
+  WS<float> w;
+  ws_carve<float>(m, &w, smem + (size_t)wib * a.ws_bytes);
+  LockQueue& Q = *reinterpret_cast<LockQueue*>(smem + (size_t)wpb * a.ws_bytes);
+  if (threadIdx.x < 4) Q.cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int nobs = m.nq + m.nv;
+  const int qcap = wpb * HSR_MAXJOBS;
+  for (int env0 = blockIdx.x * wpb; env0 < a.n; env0 += gridDim.x * wpb) {
+    const int env = env0 + wib;
+    const bool valid = env < a.n;
+    if (valid) {
+      load_state<32>(a, w, g, env);
+      for (int i = g.lane; i < m.nu; i += 32) w.ctrl[i] = a.ctrl ? a.ctrl[(size_t)env * m.nu + i] : 0.f;
+    }
+    g.sync();
+    bool success = false, finished = !valid || a.nsub <= 0;
+    int taken = 0;
+    for (int sb = 0; sb < a.nsub; sb++) {
+      if (__syncthreads_and(finished)) break;
+      int nlimit = 0, nrow = 0, ncon = 0, it0 = 0, ls0 = 0;
+      if (!finished) {
+        HSR_PHASE_START(w, g);
+        kinematics_trig(m, w, g);
+        if (g.lane == 0) kinematics_lane0(m, w);
+        g.sync();
+        HSR_PHASE(w, g, PH_KIN);
+        cdof_geoms(m, w, g);
+        g.sync();
+        mass_matrix(m, w, g);
+        g.sync();
+        HSR_PHASE(w, g, PH_CRB);
+        if (g.lane == 0) smooth_lane0(m, w);
+        g.sync();
+        smooth_solve(m, w, g);
+        HSR_PHASE(w, g, PH_SMOOTH);
+        for (int j = 0; j < m.njnt; j++) {
+          if (!m.jnt_limited[j] || m.jnt_type[j] == JNT_FREE) continue;
+          const float q = w.qpos[m.jnt_qposadr[j]];
+          if (q - m.jnt_range[2 * j] < 0) nlimit++;
+          if (m.jnt_range[2 * j + 1] - q < 0) nlimit++;
+        }
+        nrow = nlimit;
+        collision_cull(m, w, g);
+        // queue the convex-convex candidates: long jobs (no cached separating direction) from the front, quick ones from the back
+        if (g.lane == 0) {
+          int kc = 0;
+          for (int base = 0; base < m.npair; base += 32) {
+            unsigned bb = w.cand[base >> 5];
+            while (bb) {
+              const int pk = base + __ffs((int)bb) - 1;
+              bb &= bb - 1;
+              if (m.pair_func[pk] != NP_CONVEX_CONVEX) continue;
+              if (kc < HSR_MAXJOBS) {
+                const int code = (wib << 16) | (kc << 8) | pk;
+                if (w.sep[4 * pk + 3] == 1.f) Q.jobs[qcap - 1 - atomicAdd(&Q.cnt[1], 1)] = code;
+                else Q.jobs[atomicAdd(&Q.cnt[0], 1)] = code;
+              }
+              kc++;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      {
+        // every warp serves jobs: the owner's poses and separating-direction cache, this warp's registers
+        const int nlong = Q.cnt[0], njobs = nlong + Q.cnt[1];
+        while (true) {
+          int j = 0;
+          if (g.lane == 0) j = atomicAdd(&Q.cnt[2], 1);
+          j = __shfl_sync(0xffffffffu, j, 0);
+          if (j >= njobs) break;
+          const int code = j < nlong ? Q.jobs[j] : Q.jobs[qcap - 1 - (j - nlong)];
+          const int pk = code & 255;
+          WS<float> wo;
+          ws_carve<float>(m, &wo, smem + (size_t)(code >> 16) * a.ws_bytes);
+          Geom<float> A, B;
+          load_geom(m, wo, m.pair_geom1[pk], A);
+          load_geom(m, wo, m.pair_geom2[pk], B);
+          GT depth = 0; V3<GT> dir = mk<GT>(0, 0, 1), pos = mk<GT>(0, 0, 0);
+          const bool hit = mpr_penetration_inl(A, B, (GT)m.mpr_tolerance, m.mpr_iterations, g, depth, dir, pos, wo.sep + 4 * pk);
+          if (g.lane == 0) {
+            GT* r = wo.jres + 8 * ((code >> 8) & 255);
+            r[0] = hit ? 1.0 : 0.0; r[1] = depth; r[2] = dir.x; r[3] = dir.y; r[4] = dir.z; r[5] = pos.x; r[6] = pos.y; r[7] = pos.z;
+          }
+          g.sync();
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 3) Q.cnt[threadIdx.x] = 0;
+      if (!finished) {
+        ncon = collision_assemble(m, w, g, nrow);
+        g.sync();
+        HSR_PHASE(w, g, PH_COLLIDE);
+        make_constraint(m, w, g, nlimit, ncon);
+        it0 = w.wi[WI_ITER]; ls0 = w.wi[WI_LSEVAL];
+        g.sync();
+        if (g.lane == 0) { w.wi[WI_NCON] = ncon; w.wi[WI_NEFC] = nrow; w.wi[WI_NLIMIT] = nlimit; }
+        g.sync();
+        HSR_PHASE(w, g, PH_ROWS);
+        solve_newton(m, w, g, nlimit, ncon, nrow);
+        HSR_PHASE(w, g, PH_SOLVE);
+        if (g.lane == 0) {
+          w.wi[WI_SUMCON] += ncon; w.wi[WI_SUMEFC] += nrow;
+          w.wi[WI_KFLOP] += algorithmic_flops(m, ncon, nrow, w.wi[WI_ITER] - it0, w.wi[WI_LSEVAL] - ls0, w.wi[WI_NPFLOP]);
+        }
+        g.sync();
+      }
+      __syncthreads();
+      if (!finished) {
+        euler_solve(m, w, g);
+        if (g.lane == 0) euler_lane0(m, w);
+        g.sync();
+        HSR_PHASE(w, g, PH_EULER);
+        taken++;
+        if (goal_reached(m, a.cfg, w)) success = true;
+        if (success || sb == a.nsub - 1) finished = true;
+      }
+    }
+    if (valid) {
+      store_state<32>(a, w, g, env);
+      if (a.obs) for (int i = g.lane; i < nobs; i += 32) a.obs[(size_t)env * nobs + i] = w.qpos[i];
+      if (g.lane == 0) {
+        const int flags = w.wi[WI_FLAGS];
+        if (a.reward) a.reward[env] = success ? 1.0f : 0.0f;
+        if (a.done) a.done[env] = success ? 1 : 0;
+        if (a.success) a.success[env] = success ? 1 : 0;
+        if (a.taken) a.taken[env] = taken;
+        if (a.bad) a.bad[env] = (unsigned char)flags;
+        atomicAdd(a.stats + ST_SUBSTEPS, (unsigned long long)taken);
+        atomicAdd(a.stats + ST_ITERS, (unsigned long long)w.wi[WI_ITER]);
+        atomicAdd(a.stats + ST_NARROW, (unsigned long long)w.wi[WI_NARROW]);
+        atomicAdd(a.stats + ST_LSEVAL, (unsigned long long)w.wi[WI_LSEVAL]);
+        atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)w.wi[WI_SUMCON]);
+        atomicAdd(a.stats + ST_ROWS, (unsigned long long)w.wi[WI_SUMEFC]);
+        atomicAdd(a.stats + ST_FLOPS, (unsigned long long)w.wi[WI_KFLOP]);
+#ifdef HSRB_PHASE_CLOCKS
+        for (int k = 0; k < PH_COUNT; k++) atomicAdd(a.stats + ST_PHASE0 + k, (unsigned long long)w.wi[WI_PHASE0 + k]);
+#endif
+        if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
+      }
+    }
+    __syncthreads();
+  }
+}
+#endif  // HSRB_STEP_LOCK_IMPL
+cudaError_t hsrb_prepare_step_lock(size_t smem, int threads, int* blocks_per_sm);
+cudaError_t hsrb_launch_step_lock(const KArgs& a, int grid, int threads, size_t smem, cudaStream_t s);
 
 // per-G entry points, one translation unit each (parallel compilation)
 #define HSRB_DECL_G(G)                                                \

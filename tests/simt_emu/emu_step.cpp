@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 
+#define HSRB_STEP_LOCK_IMPL 1
 #include "../../hsr_env_b200/csrc/hsrb_kernels.cuh"
 
 namespace {
@@ -39,11 +40,15 @@ extern "C" int emu_general_step(const void* blob, size_t bytes, int G, int n, in
   a.ws_bytes = (unsigned)ws_carve<float>(a.m, nullptr, nullptr);
   a.state = state.data(); a.ctrl = c32.data(); a.obs = obs.data(); a.reward = reward.data(); a.done = done.data();
   a.success = succ.data(); a.taken = tk.data(); a.bad = bad.data(); a.stats = stats.data();
-  const int gpb = 32 / G;
+  if (G == 0) {   // the phase-locked kernel: one warp per environment, 3 warps per block
+    const int wpb = 3;
+    emu::launch((n + wpb - 1) / wpb, 32 * wpb, (size_t)a.ws_bytes * wpb + lock_tail_bytes(), [&]() { hsrb_step_lock_kernel(a); });
+  }
+  const int gpb = G ? 32 / G : 1;
   const int grid = (n + gpb - 1) / gpb;
   const size_t smem = (size_t)a.ws_bytes * gpb;
   if (G == 4) run<4>(a, grid, smem); else if (G == 8) run<8>(a, grid, smem); else if (G == 16) run<16>(a, grid, smem);
-  else if (G == 32) run<32>(a, grid, smem); else return -3;
+  else if (G == 32) run<32>(a, grid, smem); else if (G != 0) return -3;
   for (int e = 0; e < n; e++) {
     const float* st = state.data() + (size_t)e * S;
     for (int i = 0; i < m.nq; i++) qpos_o[(size_t)e * m.nq + i] = st[i];
