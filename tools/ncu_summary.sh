@@ -16,4 +16,4 @@ tot=sum(vals.values())
 print(' '.join('%s %.3f'%(k, v/tot) for k,v in sorted(vals.items(), key=lambda kv:-kv[1])[:9]))
 "
 ncu -i $REP --page source --csv --print-source cuda,sass > /tmp/_src.csv 2>/dev/null
-python /tmp/regions.py /tmp/_src.csv $UNIT | head -${3:-32}
+python tools/ncu_regions_wpe.py /tmp/_src.csv $UNIT | head -${3:-32}
