@@ -8,6 +8,7 @@
 // Replaces mujoco_py.load_model_from_path / MjSim / sim.step / sim.reset / sim.forward / get_state /
 // set_state as used by /root/reference/hsr/mujoco_env.py:33-34,83-94 and /root/reference/hsr/env.py:115-177.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdarg>
 #include <cstdlib>
@@ -81,9 +82,17 @@ struct hsrb {
   bool wpe_ok = false, wpe_configured = false;
   int wpe_threads = 0, wpe_grid = 0, wpe_bps = 0;
   unsigned wpe_ws = 0;
+  // work-sorted launch order of the wpe kernel: the kernel writes a work estimate per environment, the next launch takes
+  // the environments heaviest first (slot r -> block r % grid, warp r / grid: the heaviest warps of every block form team 0)
+  int *d_work = nullptr, *d_work_sorted = nullptr, *d_iota = nullptr, *d_order = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  bool order_valid = false;
 };
 
 namespace {
+
+__global__ void fill_iota(int* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 
 cudaError_t prepare(int G, size_t smem, int* bps) {
   switch (G) {
@@ -210,6 +219,7 @@ int configure_wpe(hsrb* h) {
   const int need = (h->n + wpb - 1) / wpb;
   const int cap = h->wpe_bps * h->num_sm;
   h->wpe_grid = need < cap ? need : cap;
+  if (const char* o = getenv("HSRB_WPE_GRID")) { int v = atoi(o); if (v >= 1 && v < h->wpe_grid) h->wpe_grid = v; }   // experiments
   h->wpe_configured = true;
   return 0;
 }
@@ -263,7 +273,24 @@ int run(hsrb* h, KArgs& a, void* stream) {
     const bool lock = !(lk && lk[0] == '0');
     const unsigned teams = tm ? (unsigned)atoi(tm) : 2u;
     if (!(a.opts & 0xf0u)) a.opts |= (teams & 15u) << 4;
+    const char* so = getenv("HSRB_WPE_SORT");
+    const bool sorted = !(so && so[0] == '0');
+    if (sorted && !h->d_work) {
+      const size_t nb = sizeof(int) * (size_t)h->n;
+      CU(cudaMalloc(&h->d_work, nb)); CU(cudaMalloc(&h->d_work_sorted, nb)); CU(cudaMalloc(&h->d_iota, nb)); CU(cudaMalloc(&h->d_order, nb));
+      CU(cudaMemsetAsync(h->d_work, 0, nb, (cudaStream_t)stream));
+      fill_iota<<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_iota, h->n);
+      CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_work, h->d_work_sorted, h->d_iota, h->d_order, h->n, 0, 24,
+                                                   (cudaStream_t)stream));
+      CU(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+    }
+    if (sorted) { a.work = h->d_work; a.order = h->order_valid ? h->d_order : nullptr; }
     CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream, lock));
+    if (sorted) {   // the next launch's order (stable radix sort: ties keep the environment order)
+      CU(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_work, h->d_work_sorted, h->d_iota, h->d_order, h->n, 0, 24,
+                                                   (cudaStream_t)stream));
+      h->order_valid = true;
+    }
     h->launches++;
     return 0;
   }
@@ -411,6 +438,7 @@ int hsrb_destroy(hsrb_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->d_fast_tab); cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_episode); cudaFree(h->d_stats);
+  cudaFree(h->d_work); cudaFree(h->d_work_sorted); cudaFree(h->d_iota); cudaFree(h->d_order); cudaFree(h->d_sort_tmp);
   cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_taken);
   delete h;
   return 0;
@@ -497,6 +525,15 @@ int hsrb_set_starts(hsrb_t* h, int nstart, const int32_t* qpos_adr, const int32_
   }
   return 0;
 }
+
+#if defined(WPE_CHAIN_CLOCKS)
+// experiment hook (not part of include/hsrb.h): the per-environment work array of the last wpe launch -> host
+extern "C" int hsrb_debug_work(hsrb_t* h, int* out_host) {
+  if (!h || !h->d_work) return -1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out_host, h->d_work, sizeof(int) * (size_t)h->n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int hsrb_reset(hsrb_t* h, const uint8_t* mask, float* obs, void* stream) {
   if (!h) return fail(-1, "null handle");

@@ -37,6 +37,8 @@ struct KArgs {
   float* body_xpos; float* gripper;
   double* dump; unsigned dump_stride;
   unsigned long long* stats;
+  const int* order;        // wpe kernel: environment of launch slot r (heaviest first), or null = identity
+  int* work;               // wpe kernel: [N] work estimate of this action per environment (the next launch's sort key)
 };
 
 enum { MODE_STEP = 0, MODE_DEBUG = 1, MODE_FORWARD = 2, MODE_RESET = 3 };

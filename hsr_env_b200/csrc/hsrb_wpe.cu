@@ -15,3 +15,15 @@ cudaError_t hsrb_wpe_launch(const KArgs& a, const PushInfo& f, int grid, int thr
   else hsrb_wpe_kernel_t<false><<<grid, threads, smem, s>>>(a, f);
   return cudaGetLastError();
 }
+
+#if defined(WPE_CHAIN_CLOCKS)
+// experiment hook (not part of include/hsrb.h): out[0..31] = cycles, out[32..63] = occurrences per chain section; resets
+extern "C" int hsrb_debug_chain_clocks(unsigned long long* out) {
+  unsigned long long z[32] = {0};
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, wpe::wpe_ck_cyc, sizeof(z)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out + 32, wpe::wpe_ck_cnt, sizeof(z)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(wpe::wpe_ck_cyc, z, sizeof(z)); cudaMemcpyToSymbol(wpe::wpe_ck_cnt, z, sizeof(z));
+  return 0;
+}
+#endif

@@ -87,6 +87,20 @@ namespace wpe {
 
 typedef V3<double> V3d;
 
+// -DWPE_CHAIN_CLOCKS: cycle counters of the sections of ONE environment's dependent chain (lane 0 of every warp, clock64
+// deltas accumulated with fire-and-forget atomics); read with hsrb_debug_chain_clocks().  Meant for the free-running
+// variant with one warp per SM (n = 148), where a section's cycles are its latency without contention.
+#if defined(WPE_CHAIN_CLOCKS)
+__device__ unsigned long long wpe_ck_cyc[32], wpe_ck_cnt[32];
+#define WPE_CK_DECL long long ck_last = clock64()
+#define WPE_CK_RESET() do { ck_last = clock64(); } while (0)
+#define WPE_CK(id) do { if ((threadIdx.x & 31) == 0) { const long long t_ = clock64(); atomicAdd(&wpe::wpe_ck_cyc[id], (unsigned long long)(t_ - ck_last)); atomicAdd(&wpe::wpe_ck_cnt[id], 1ull); } ck_last = clock64(); } while (0)
+#else
+#define WPE_CK_DECL do { } while (0)
+#define WPE_CK_RESET() do { } while (0)
+#define WPE_CK(id) do { } while (0)
+#endif
+
 // Barriers of a TEAM of warps (phase-locked variant): the block's warps form 1, 2 or 4 teams that lock-step
 // independently of each other (named barriers 1 + team), so that while one team waits for its slowest member the others
 // keep the SM busy.  nthreads = warps of the team x 32.
@@ -181,8 +195,9 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
     __syncwarp();
   }
   int guard = 0, it = 0;
+  WPE_CK_DECL;
 // publish the next direction and go round again
-#define WPE_NEXT_DIR() { __syncwarp(); if (lane == 0) st3(P + 45, d); __syncwarp(); continue; }
+#define WPE_NEXT_DIR() { __syncwarp(); if (lane == 0) st3(P + 45, d); __syncwarp(); WPE_CK(21); continue; }
 #pragma unroll 1
   while (true) {
     // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along the direction in P[45..47].  Nothing
@@ -199,6 +214,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       if (lane == 0) { st3(P + 42, a2); st3(P + 36, ld3(P + 39) - a2); }
       __syncwarp();
     }
+    WPE_CK(20);
     const V3d v4 = ld3(P + 36);
     V3d d = ld3(P + 45);
     const V3d v0 = ld3(P);
@@ -407,9 +423,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
 #endif
 
 #pragma unroll 1
-  for (int env0 = blockIdx.x * wpb; env0 < a.n; env0 += gridDim.x * wpb) {
-    const int env = env0 + wib;
-    const bool valid = env < a.n;
+  for (int wave0 = 0; wave0 < a.n; wave0 += gridDim.x * wpb) {
+    // launch slot r -> block r % grid, warp r / grid: with a.order sorted by predicted work (heaviest first) the warps of a
+    // block are ordered by weight, so the heavy environments of the block share a team and the light teams do not wait for them
+    const int slot = wave0 + wib * (int)gridDim.x + (int)blockIdx.x;
+    const bool valid = slot < a.n;
+    const int env = valid ? (a.order ? a.order[slot] : slot) : 0;
     if (!LOCK && !valid) break;
     // ------------------------------------------------------------------ state -> shared memory
     if (valid) {
@@ -429,6 +448,10 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       if (lane < 9) s.Rb[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
     }
     int n_iter = 0, n_ls = 0, sumcon = 0, sumefc = 0, kflop = 0, flags = 0, narrow_tot = 0;
+#if defined(WPE_CHAIN_CLOCKS)
+    const long long ck_env0 = clock64();
+#endif
+    int nhit_cc = 0;   // convex-convex contacts over the action (full portal refinements: the long narrowphase jobs)
     bool success = false;
     int taken = 0;
     bool finished = !valid || a.nsub <= 0;
@@ -444,6 +467,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       int nlimit = 0, ncon = 0, nefc = 0, narrow = 0, npflop = 0, ngrp = 0, nslot = 0, gdim = 0;
       unsigned bits = 0;                // candidate pairs of this environment that passed the cull
       int it = 0, ls_used = 0;
+      WPE_CK_DECL;
       if (!finished) {
       // ---------------------------------------------------------------- poses (B.1), geometry in double
       if (HASB) {
@@ -484,6 +508,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         }
       }
       __syncwarp();
+      WPE_CK(0);
       // ---------------------------------------------------------------- active joint limits: groups 0 .. nlimit-1
       {
         bool act = false;
@@ -538,6 +563,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         }
         bits = __ballot_sync(FULL, hit);
       }
+      WPE_CK(1);
       if (LOCK && lane == 0) {
         // queue this environment's convex-convex candidates for the block's warps: a pair without a cached separating
         // direction (in contact last time, or new) is a full refinement (~11 support evaluations) and goes to the front,
@@ -639,11 +665,13 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
             }
             if (nh > room) { nh = room; flags |= FLAG_CON_OVERFLOW; }
             ncon += nh; nefc += nh * dim;
+            WPE_CK(2);
           } else if (func == NP_CONVEX_CONVEX && LOCK && kc < WPE_ENVJOBS) {
             // the job's result record (written by the warp that served it)
             const float* r = s.jres + 14 * kc;
             kc++;
             if (r[0] != 0.f) {
+              nhit_cc++;
               if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
               else {
                 if (lane == 0) s.con_pair[ncon] = pk;
@@ -656,6 +684,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           } else if (func == NP_CONVEX_CONVEX || func == NP_PLANE_CONVEX) {
             bool hitc;
             kc++;
+            WPE_CK_RESET();
+            const float sf_ = use_sep ? s.sep[4 * pk + 3] : 0.f;
             if (func == NP_PLANE_CONVEX) {
               const double* Ma = t.gmatw + 9 * ga;
               const wpe::V3d n = mk<double>(Ma[2], Ma[5], Ma[8]);
@@ -670,6 +700,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
               hitc = wpe::mpr(t, s, s, verts4, ga, gb, gb0, (double)m.mpr_tolerance, m.mpr_iterations, use_sep ? s.sep + 4 * pk : nullptr);
             }
             if (hitc) {
+              if (func == NP_CONVEX_CONVEX) nhit_cc++;
               if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
               else {
                 if (lane == 0) {
@@ -681,6 +712,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
                 ncon++; nefc += dim;
               }
             }
+            WPE_CK(hitc ? 3 : (sf_ == 1.f ? 4 : 5));
           } else {   // box-box (block against the pan): hsr_core.h, rare
             WS<float> w;                                // view for hsr::box_box / add_contact
             w.gpos = s.gpos; w.gaabb = nullptr; w.con_dist = s.con_dist; w.con_pos = s.con_pos; w.con_frame = s.con_frame;
@@ -699,6 +731,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
             nefc = nrow_;
             __syncwarp();
             flags |= s.wi[WI_FLAGS];
+            WPE_CK(18);
           }
         }
       }
@@ -708,6 +741,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       nslot = 6 * ngrp;
       sumcon += ncon; sumefc += nefc;
 
+      WPE_CK_RESET();
       // ---------------------------------------------------------------- smooth forces (closed form, B.6): dof lanes
       if (lane < 8) {
         float q = 0.f;
@@ -734,6 +768,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         s.qs[lane] = q;
         s.as[lane] = lane < NV ? q / fi.Mdiag[lane] : 0.f;
       }
+      WPE_CK(6);
       // ---------------------------------------------------------------- constraint rows: one contact per group lane (B.4/B.5)
       if (lane < nlimit) gdim = 1;
       else if (lane < ngrp) {
@@ -800,6 +835,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         }
       }
       __syncwarp();
+      WPE_CK(7);
 
       // ---------------------------------------------------------------- Newton solver (B.7)
       // One loop whose body appears once in the instruction stream: [rows at the point] -> cost / forces / zones ->
@@ -838,6 +874,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
               s.jar[r] = acc;
             }
             __syncwarp();
+            WPE_CK(8);
           }
           // ---- cost of the point: Gauss term on the dof lanes, cone / half-line state of each group on its lane
           //      (zone, forces -> s.f)
@@ -885,6 +922,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           }
           const float c = wpe::warp_sum(cl);
           __syncwarp();
+          WPE_CK(9);
           if (phase == 0) { cs = c; xp = s.warm; phase = 1; continue; }
           if (phase == 1) {
             const bool use_warm = c <= cs;   // ties -> warm start
@@ -914,6 +952,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
 #pragma unroll
           for (int o = 1; o < 8; o <<= 1) gn += __shfl_xor_sync(FULL, gn, o);
           gn = sqrtf(gn);
+          WPE_CK(10);
           if (finishing || (it > 0 && scale * gn < m.tolerance) || it >= m.iterations) {
             if (lane < 8) s.qfc[lane] = qf;
             solving = false;
@@ -981,6 +1020,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           }
 #pragma unroll
           for (int j = 0; j < 8; j++) if (li == j) Hr[j] += Mi;
+          WPE_CK(11);
           // ---- Cholesky H = L L^T: lane i holds row i; column k is finished by a broadcast of the pivot and one
           //      shuffle per trailing column (the four 8-lane segments of the warp work redundantly)
           float inv_diag = 1.f;
@@ -1030,6 +1070,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           }
           sn = sqrtf(sn);
           __syncwarp();
+          WPE_CK(12);
           if (!(sn >= 1e-15f)) {
             if (lane < 8) s.qfc[lane] = qf;
             solving = false;
@@ -1069,6 +1110,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           {
             // At alpha = 0 the derivative along the Newton direction is grad . s = -dec and its slope s^T H s = dec (H s = -grad):
             // no evaluation needed; the first trial point is the full Newton step.
+            WPE_CK(13);
             float d1 = -dec, d2 = dec, nxt = 0.f;
             int nev = 1;
             float lo = 0.f, hi = -1.f, dlo = d1, dhi = 0.f;
@@ -1110,6 +1152,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
               else if (hi < 0 || alpha < hi) { hi = alpha; dhi = d1; }
               conv = fabsf(d1) < gtol || tiny;
               nev++;
+              WPE_CK(14);
             }
             ls_used += nev;
             if (!conv) {
@@ -1125,6 +1168,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           if (lane < 8) s.x[lane] += alpha * s.srch[lane];
           for (int r = lane; r < nslot; r += 32) s.jar[r] += alpha * s.jv[r];
           __syncwarp();
+          WPE_CK(16);
         }
         __syncwarp();
       }
@@ -1132,6 +1176,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       if (LOCK) wpe::team_sync(team, tthreads);
       WPE_PH(PH_SOLVE);
       if (!finished) {
+      WPE_CK_RESET();
       n_iter += it; n_ls += ls_used;
       kflop += algorithmic_flops(m, false, ncon, nefc, it, ls_used, npflop);   // slides + free box: M is constant
 
@@ -1178,6 +1223,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         if (lane < 4) s.qpos[5 + lane] = qq[lane];
         __syncwarp();
       }
+      WPE_CK(17);
       taken++;
       if (reached) success = true;
       if (reached || sb_ == a.nsub - 1) finished = true;
@@ -1200,6 +1246,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         if (a.success) a.success[env] = success ? 1 : 0;
         if (a.taken) a.taken[env] = taken;
         if (a.bad) a.bad[env] = (unsigned char)flags;
+        // work estimate in k-cycles of an uncontended warp (tools/chain_clocks.py): fixed part, Newton iterations, refinements, rows
+#if defined(WPE_CHAIN_CLOCKS)
+        if (a.work) a.work[env] = (int)((clock64() - ck_env0) >> 10);   // measured: k-cycles of this environment's action
+#else
+        if (a.work) a.work[env] = 20 * taken + 7 * n_iter + 30 * nhit_cc + sumcon;
+#endif
         atomicAdd(a.stats + ST_SUBSTEPS, (unsigned long long)taken);
         atomicAdd(a.stats + ST_ITERS, (unsigned long long)n_iter);
         atomicAdd(a.stats + ST_NARROW, (unsigned long long)narrow_tot);

@@ -430,3 +430,32 @@ def test_wpe_kernel_variants_are_bitwise_identical(monkeypatch):
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b)
     assert int(outs[0][3].sum()) == 0 and np.isfinite(outs[0][0]).all()
+
+
+def test_wpe_work_sorted_launch_order_does_not_change_results(monkeypatch):
+    """The wpe kernel takes the environments heaviest-first from the second launch on (order = radix sort of the work
+    estimates the previous launch wrote): which warp of which block steps an environment changes, its arithmetic does
+    not.  Three actions with the sort on and off: same bits; with it on, the launch order really is a permutation."""
+    from hsr_env_b200.env import BatchedHSREnv
+    from hsr_env_b200.spaces import Box
+    from hsr_env_b200.util import GoalSpec
+    from scenarios import BLOCK_HI, BLOCK_LO, GOAL_HI, GOAL_LO
+
+    goals = [GoalSpec(Box(BLOCK_LO, BLOCK_HI), Box(GOAL_LO, GOAL_HI), .05)]
+    n = 4100   # not a multiple of the 28 warps of a block: the last launch slots are empty
+    acts = torch.rand(3, n, 2, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    outs = []
+    for sort in ("0", "1"):
+        monkeypatch.setenv("HSRB_WPE_SORT", sort)
+        env = BatchedHSREnv("c2_push.hsrb", goals, n_envs=n, device="cuda:0", seed=5, kernel="wpe")
+        env.reset()
+        res = []
+        for k in range(3):
+            obs, reward, done, info = env.step(acts[k])
+            res += [obs.cpu().numpy(), done.cpu().numpy(), info["substeps_taken"].cpu().numpy(), info["bad_state"].cpu().numpy()]
+            env.reset(mask=done)
+        outs.append(res)
+        env.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert int(sum(int(x.sum()) for x in outs[0][3::4])) == 0
