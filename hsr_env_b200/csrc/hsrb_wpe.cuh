@@ -135,6 +135,7 @@ __device__ __forceinline__ const double* geom_mat(const Tab& t, const Slice& s, 
 // (same arithmetic as hsr::support_d)
 // (s: the slice of the environment the geom belongs to)
 __device__ __noinline__ V3d support(const Tab& t, const Slice& s, const float* verts4, int gi, int gb0, V3d d) {
+  WPE_CK_DECL;
   const double* R = geom_mat(t, s, gi, gb0);
   const V3d dl = multv(R, d);
   const int type = t.geom_type[gi];
@@ -151,10 +152,14 @@ __device__ __noinline__ V3d support(const Tab& t, const Slice& s, const float* v
   } else {
     const DevGrp<32> gw;
     const float* v4 = verts4 + 4 * t.geom_vertadr[gi];
+    WPE_CK(22);
     const int bi = hull_argmax<float>(v4, 4, t.geom_vertnum[gi], dl, gw);
+    WPE_CK(23);
     res = mk<double>((double)v4[4 * bi], (double)v4[4 * bi + 1], (double)v4[4 * bi + 2]);
   }
-  return ld3(s.gpos + 3 * gi) + mulv(R, res);
+  const V3d out_ = ld3(s.gpos + 3 * gi) + mulv(R, res);
+  WPE_CK(type == GEOM_BOX ? 25 : 24);
+  return out_;
 }
 
 // portal vertex k of the warp's scratch: 9 doubles  v = v1 - v2 | v1 (on geom 1) | v2 (on geom 2)
@@ -412,6 +417,14 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
   if (nteam < 1 || nteam > WPE_MAXTEAMS || wpb % nteam != 0) nteam = 1;
   const int wpt = wpb / nteam, team = wib / wpt, tthreads = 32 * wpt;
   int* const qcnt = Q.cnt[team];
+#if !defined(HSRB_SIMT_EMU)
+  // experiment: opts bits 8..15 = start stagger of team k in units of 4 us x k (teams that start in phase stay in phase on
+  // uniform work and then compete for the same pipes in every phase)
+  if (LOCK && team > 0 && ((a.opts >> 8) & 255u)) {
+    const long long t0 = clock64(), wait = (long long)((a.opts >> 8) & 255u) * 4 * 1965 * team;
+    while (clock64() - t0 < wait) __nanosleep(1000);
+  }
+#endif
   int* const qjobs = Q.jobs + team * wpt * WPE_ENVJOBS;
   const int qcap = wpt * WPE_ENVJOBS;
 #if defined(WPE_DEBUG_JOBS)
@@ -769,69 +782,62 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         s.as[lane] = lane < NV ? q / fi.Mdiag[lane] : 0.f;
       }
       WPE_CK(6);
-      // ---------------------------------------------------------------- constraint rows: one contact per group lane (B.4/B.5)
+      // ---------------------------------------------------------------- constraint rows (B.4/B.5): lane = (contact, row), five contacts per round
       if (lane < nlimit) gdim = 1;
-      else if (lane < ngrp) {
-        const int c = lane - nlimit;
-        const int pk = s.con_pair[c];
-        gdim = t.pair_condim[pk];
-        const float sr = t.pair_sr[pk], sbk = t.pair_sb[pk];
-        const float* fr = s.con_frame + 9 * c;
-        const float* fri = t.pair_friction + 5 * pk;
-        float rel[3] = {0.f, 0.f, 0.f};
-        if (HASB) {
+      else if (lane < ngrp) gdim = t.pair_condim[s.con_pair[lane - nlimit]];
+      {
+        const int cl = (lane * 43) >> 8, r = lane - 6 * cl;   // lane / 6, lane % 6
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncon; c0 += 5) {
+          const int c = c0 + cl;
+          if (lane < 30 && c < ncon) {
+            const int pk = s.con_pair[c];
+            const int gd = t.pair_condim[pk];
+            float Jr[8];
 #pragma unroll
-          for (int q = 0; q < 3; q++) rel[q] = (float)((double)s.con_pos[3 * c + q] - s.xb[q]);
-        }
-        const double* pc = t.pairc + PUSH_PAIRC * pk;
-        const double dist = (double)s.con_dist[c];
-        const double imp = push::impedance5<true>(pc + 3, dist);
-        const float D0 = (float)fmin(1e15, imp / ((1 - imp) * pc[2]));   // 1 / max(1e-15, R0)
-        const float D1 = D0 * m.impratio;
-        const float mu = gdim > 1 ? fri[0] * rsqrtf(m.impratio) : 1.f;   // fri0 * sqrt(R1 / R0); one-row contact: plain row
-        const push::F8 qv8 = push::ld8(s.qvel);
-        float ax[9];   // body axes of the block in the world frame (columns of Rb)
-#pragma unroll
-        for (int q = 0; q < 9; q++) ax[q] = (float)s.Rb[q];
-        const int gslot = 6 * lane;
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-          float Jr[8];
-#pragma unroll
-          for (int d = 0; d < 8; d++) Jr[d] = 0.f;
-          float Dv = 0.f, ar = 0.f, rs = 0.f;
-          if (r < gdim) {
-            const float* frr = fr + 3 * (r < 3 ? r : r - 3);
-            const float f0 = frr[0], f1 = frr[1], f2 = frr[2];
-            if (r < 3) {
-#pragma unroll
-              for (int j = 0; j < 2; j++) Jr[j] = sr * (f0 * fi.axis[j][0] + f1 * fi.axis[j][1] + f2 * fi.axis[j][2]);
-            }
-            if (HASB) {
-#pragma unroll
-              for (int q = 0; q < 3; q++) {
-                const float ax0 = ax[q], ax1 = ax[3 + q], ax2 = ax[6 + q];  // body axis q, world frame
-                if (r < 3) {
-                  const float jp0 = ax1 * rel[2] - ax2 * rel[1], jp1 = ax2 * rel[0] - ax0 * rel[2], jp2 = ax0 * rel[1] - ax1 * rel[0];
-                  Jr[2 + q] = sbk * (q == 0 ? f0 : (q == 1 ? f1 : f2));
-                  Jr[5 + q] = sbk * (f0 * jp0 + f1 * jp1 + f2 * jp2);
-                } else {
-                  Jr[5 + q] = sbk * (f0 * ax0 + f1 * ax1 + f2 * ax2);
+            for (int d = 0; d < 8; d++) Jr[d] = 0.f;
+            float Dv = 0.f, ar = 0.f, rs = 0.f;
+            if (r < gd) {
+              const float sr = t.pair_sr[pk], sbk = t.pair_sb[pk];
+              const float* frr = s.con_frame + 9 * c + 3 * (r < 3 ? r : r - 3);
+              const float f0 = frr[0], f1 = frr[1], f2 = frr[2];
+              const float* fri = t.pair_friction + 5 * pk;
+              const double* pc = t.pairc + PUSH_PAIRC * pk;
+              const double dist = (double)s.con_dist[c];
+              const double imp = push::impedance5<true>(pc + 3, dist);
+              const float D0 = (float)fmin(1e15, imp / ((1 - imp) * pc[2]));   // 1 / max(1e-15, R0)
+              const float D1 = D0 * m.impratio;
+              float w0 = f0, w1 = f1, w2 = f2;   // rotational rows: the frame axis itself; translational: rel x f
+              if (r < 3) {
+                Jr[0] = sr * (f0 * fi.axis[0][0] + f1 * fi.axis[0][1] + f2 * fi.axis[0][2]);
+                Jr[1] = sr * (f0 * fi.axis[1][0] + f1 * fi.axis[1][1] + f2 * fi.axis[1][2]);
+                if (HASB) {
+                  const float r0 = (float)((double)s.con_pos[3 * c] - s.xb[0]), r1 = (float)((double)s.con_pos[3 * c + 1] - s.xb[1]),
+                              r2 = (float)((double)s.con_pos[3 * c + 2] - s.xb[2]);
+                  Jr[2] = sbk * f0; Jr[3] = sbk * f1; Jr[4] = sbk * f2;
+                  w0 = r1 * f2 - r2 * f1; w1 = r2 * f0 - r0 * f2; w2 = r0 * f1 - r1 * f0;   // f . (axis x rel) = axis . (rel x f)
                 }
               }
-            }
-            float vel = 0.f;
+              if (HASB) {
 #pragma unroll
-            for (int d = 0; d < 8; d++) vel += Jr[d] * qv8.v[d];
-            if (r == 0) { Dv = D0; ar = (float)(-pc[1] * (double)vel - pc[0] * imp * dist); rs = mu; }
-            else {
-              ar = (float)(-pc[1] * (double)vel);
-              Dv = r == 1 ? D1 : D1 * (fri[r - 1] * fri[r - 1]) / (fri[0] * fri[0]);
-              rs = fri[r - 1];
+                for (int q = 0; q < 3; q++)   // body axis q of the block in the world frame = column q of Rb
+                  Jr[5 + q] = sbk * ((float)s.Rb[q] * w0 + (float)s.Rb[3 + q] * w1 + (float)s.Rb[6 + q] * w2);
+              }
+              const push::F8 qv8 = push::ld8(s.qvel);
+              float vel = 0.f;
+#pragma unroll
+              for (int d = 0; d < 8; d++) vel += Jr[d] * qv8.v[d];
+              if (r == 0) { Dv = D0; ar = (float)(-pc[1] * (double)vel - pc[0] * imp * dist); rs = gd > 1 ? fri[0] * rsqrtf(m.impratio) : 1.f; }   // rs: mu = fri0 * sqrt(R1 / R0)
+              else {
+                ar = (float)(-pc[1] * (double)vel);
+                Dv = r == 1 ? D1 : D1 * (fri[r - 1] * fri[r - 1]) / (fri[0] * fri[0]);
+                rs = fri[r - 1];
+              }
             }
+            const int slot_ = 6 * (nlimit + c) + r;
+            push::st8(s.J + 8 * slot_, Jr);
+            s.Dr[slot_] = Dv; s.aref[slot_] = ar; s.rsc[slot_] = rs;
           }
-          push::st8(s.J + 8 * (gslot + r), Jr);
-          s.Dr[gslot + r] = Dv; s.aref[gslot + r] = ar; s.rsc[gslot + r] = rs;
         }
       }
       __syncwarp();
@@ -851,8 +857,8 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         int zone = 0;
         float cN = 0.f, cT = 0.f;
         int phase = 0;
-        const float* xp = s.as;
-        float cs = 0.f, cost = 0.f, alpha = 0.f, dec = 0.f;
+        const float* xp = s.warm;
+        float cost = 0.f, alpha = 0.f, dec = 0.f;
         bool finishing = false;   // converged by the improvement test: stop after the next gradient (forces of the final point)
 #pragma unroll 1
         while (true) {
@@ -863,7 +869,20 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           if (!solving) break;   // the warps run their passes freely inside the solver phase (one barrier after the loop)
 #endif
           if (!solving) continue;
-          if (phase < 3) {
+          const bool dual = phase == 0;   // both starting points in one pass: lanes 0..15 at qacc_warmstart, lanes 16..31 at qacc_smooth
+          if (dual) {
+            // jar = J warm - aref, and J as - aref into the (still unused) jv slots
+            const push::F8 xw = push::ld8(s.warm), xa = push::ld8(s.as);
+            for (int r = lane; r < nslot; r += 32) {
+              const push::F8 j = push::ld8(s.J + 8 * r);
+              float accw = -s.aref[r], acca = accw;
+#pragma unroll
+              for (int d = 0; d < 8; d++) { accw += j.v[d] * xw.v[d]; acca += j.v[d] * xa.v[d]; }
+              s.jar[r] = accw; s.jv[r] = acca;
+            }
+            __syncwarp();
+            WPE_CK(8);
+          } else if (phase < 3) {
             // jar = J x - aref (row slots across lanes)
             const push::F8 xv = push::ld8(xp);
             for (int r = lane; r < nslot; r += 32) {
@@ -879,15 +898,17 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           // ---- cost of the point: Gauss term on the dof lanes, cone / half-line state of each group on its lane
           //      (zone, forces -> s.f)
           float cl = 0.f;
-          if (lane < 8) { const float xi = xp[lane]; cl = 0.5f * (Mi * xi - s.qs[lane]) * (xi - s.as[lane]); }
-          if (lane < ngrp) {
-            const float* pj = s.jar + 6 * lane; const float* pD = s.Dr + 6 * lane; const float* ps = s.rsc + 6 * lane;
+          if (lane < 8) { const float xi = xp[lane]; cl = 0.5f * (Mi * xi - s.qs[lane]) * (xi - s.as[lane]); }   // zero at qacc_smooth
+          const int gl = dual ? (lane & 15) : lane;                                 // group of this lane
+          const int gd_ = dual ? __shfl_sync(FULL, gdim, lane & 15) : gdim;
+          if (gl < ngrp) {
+            const float* pj = ((dual && lane >= 16) ? s.jv : s.jar) + 6 * gl; const float* pD = s.Dr + 6 * gl; const float* ps = s.rsc + 6 * gl;
             float jr[6], Dv[6], rs[6];
 #pragma unroll
             for (int r = 0; r < 6; r++) { jr[r] = pj[r]; Dv[r] = pD[r]; rs[r] = ps[r]; }
             const float mu = rs[0];
             int z; float n_ = 0.f, t_ = 0.f;
-            if (gdim == 1) {
+            if (gd_ == 1) {
               z = jr[0] < 0 ? 1 : 0;
             } else {
               n_ = jr[0] * mu;
@@ -915,17 +936,25 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
 #pragma unroll
               for (int j = 1; j < 6; j++) fo[j] = f0t * (jr[j] * rs[j]) * rs[j];
             }
-            float* pf = s.f + 6 * lane;
+            if (lane < 16) {   // (the qacc_smooth half of a dual pass only needs the cost)
+              float* pf = s.f + 6 * gl;
 #pragma unroll
-            for (int r = 0; r < 6; r++) pf[r] = fo[r];
+              for (int r = 0; r < 6; r++) pf[r] = fo[r];
+            }
             zone = z; cN = n_; cT = t_;
           }
-          const float c = wpe::warp_sum(cl);
+          float c;
+          if (dual) {   // sums of the two half-warps
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) cl += __shfl_xor_sync(FULL, cl, o);
+            c = cl;
+          } else c = wpe::warp_sum(cl);
           __syncwarp();
           WPE_CK(9);
-          if (phase == 0) { cs = c; xp = s.warm; phase = 1; continue; }
-          if (phase == 1) {
-            const bool use_warm = c <= cs;   // ties -> warm start
+          if (dual) {
+            const float cw = __shfl_sync(FULL, c, 0), cs = __shfl_sync(FULL, c, 16);
+            c = cw;
+            const bool use_warm = cw <= cs;   // ties -> warm start
             if (lane < 8) s.x[lane] = use_warm ? s.warm[lane] : s.as[lane];
             __syncwarp();
             xp = s.x;

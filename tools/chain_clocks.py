@@ -20,7 +20,7 @@ from hsr_env_b200.util import GoalSpec
 
 NAMES = {0: "poses", 1: "limits+cull", 2: "plane-box", 3: "mpr hit", 4: "mpr miss (cached dir)", 5: "mpr miss (full)",
          6: "smooth", 7: "rows", 8: "jar (cost phases)", 9: "cost/zones", 10: "gradient", 11: "hessian", 12: "cholesky+solves",
-         13: "jv + ls coeffs", 14: "ls evaluation", 16: "update", 17: "goal+euler", 18: "box-box", 20: "support pair", 21: "portal logic"}
+         13: "jv + ls coeffs", 14: "ls evaluation", 16: "update", 17: "goal+euler", 18: "box-box", 20: "support pair", 21: "portal logic", 22: "support: setup (hull)", 23: "support: hull_argmax", 24: "support: tail (hull)", 25: "support: box total"}
 
 
 def main():
