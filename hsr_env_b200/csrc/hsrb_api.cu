@@ -251,6 +251,33 @@ bool use_lock(const hsrb* h) {
   return !(o && o[0] == '0');
 }
 
+// Work-sorted launch order of the warp-per-environment kernel (hsrb_wpe_kernel_t): the action
+// kernel writes a work estimate per environment, a radix sort (cub, descending, stable) turns it into the order of the next
+// launch.  HSRB_WPE_SORT=0 switches it off (experiments; results do not depend on it).
+bool use_sorted_order() {
+  const char* so = getenv("HSRB_WPE_SORT");
+  return !(so && so[0] == '0');
+}
+int sort_prepare(hsrb* h, KArgs& a, void* stream) {
+  if (!h->d_work) {
+    const size_t nb = sizeof(int) * (size_t)h->n;
+    CU(cudaMalloc(&h->d_work, nb)); CU(cudaMalloc(&h->d_work_sorted, nb)); CU(cudaMalloc(&h->d_iota, nb)); CU(cudaMalloc(&h->d_order, nb));
+    CU(cudaMemsetAsync(h->d_work, 0, nb, (cudaStream_t)stream));
+    fill_iota<<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_iota, h->n);
+    CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_work, h->d_work_sorted, h->d_iota, h->d_order, h->n, 0, 24,
+                                                 (cudaStream_t)stream));
+    CU(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+  }
+  a.work = h->d_work; a.order = h->order_valid ? h->d_order : nullptr;
+  return 0;
+}
+int sort_update(hsrb* h, void* stream) {   // the next launch's order (ties keep the environment order)
+  CU(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_work, h->d_work_sorted, h->d_iota, h->d_order, h->n, 0, 24,
+                                               (cudaStream_t)stream));
+  h->order_valid = true;
+  return 0;
+}
+
 KArgs base_args(hsrb* h) {
   KArgs a;
   memset(&a, 0, sizeof(a));
@@ -273,24 +300,10 @@ int run(hsrb* h, KArgs& a, void* stream) {
     const bool lock = !(lk && lk[0] == '0');
     const unsigned teams = tm ? (unsigned)atoi(tm) : 2u;
     if (!(a.opts & 0xf0u)) a.opts |= (teams & 15u) << 4;
-    const char* so = getenv("HSRB_WPE_SORT");
-    const bool sorted = !(so && so[0] == '0');
-    if (sorted && !h->d_work) {
-      const size_t nb = sizeof(int) * (size_t)h->n;
-      CU(cudaMalloc(&h->d_work, nb)); CU(cudaMalloc(&h->d_work_sorted, nb)); CU(cudaMalloc(&h->d_iota, nb)); CU(cudaMalloc(&h->d_order, nb));
-      CU(cudaMemsetAsync(h->d_work, 0, nb, (cudaStream_t)stream));
-      fill_iota<<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->d_iota, h->n);
-      CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_work, h->d_work_sorted, h->d_iota, h->d_order, h->n, 0, 24,
-                                                   (cudaStream_t)stream));
-      CU(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
-    }
-    if (sorted) { a.work = h->d_work; a.order = h->order_valid ? h->d_order : nullptr; }
+    const bool sorted = use_sorted_order();
+    if (sorted) { int rc2 = sort_prepare(h, a, stream); if (rc2) return rc2; }
     CU(hsrb_wpe_launch(a, h->fast, h->wpe_grid, h->wpe_threads, smem, (cudaStream_t)stream, lock));
-    if (sorted) {   // the next launch's order (stable radix sort: ties keep the environment order)
-      CU(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_work, h->d_work_sorted, h->d_iota, h->d_order, h->n, 0, 24,
-                                                   (cudaStream_t)stream));
-      h->order_valid = true;
-    }
+    if (sorted) { int rc2 = sort_update(h, stream); if (rc2) return rc2; }
     h->launches++;
     return 0;
   }
@@ -311,6 +324,8 @@ int run(hsrb* h, KArgs& a, void* stream) {
     a.ws_bytes = h->ws_bytes;
     a.m.ncon_max = h->dm.ncon_max; a.m.nefc_max = h->dm.nefc_max;
     const size_t smem = (size_t)h->ws_bytes * (h->lock_threads / 32) + lock_tail_bytes();
+    // (the work-sorted launch order of the wpe kernel was tried here too: no gain on configs[2] / [4], 2.80 vs 2.88 and 1.28 vs
+    // 1.35 M substeps/s - configs[2] resets every environment before every action, configs[4] runs four warps per block)
     CU(hsrb_launch_step_lock(a, h->lock_grid, h->lock_threads, smem, (cudaStream_t)stream));
     h->launches++;
     return 0;
@@ -337,6 +352,122 @@ __global__ void __launch_bounds__(1024) fma_peak_kernel(float* out, int iters, f
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
+
+// ---------------------------------------------------------------------------------------------- 'openai' observation
+// The 25-d Fetch-style observation of HSREnv._get_observation (/root/reference/hsr/env.py:72-110; the branch is dead code in
+// the snapshot, SURVEY.md App. C #8: this is its intent, stated in hsr_env_b200/kin.py, which stays as the test-side
+// oracle) from the resident state, one thread per environment, fp64: forward kinematics with 6-D body velocities down
+// the tree (bodies are in tree order), then
+//   grip_pos | object_pos | object_pos - grip_pos | finger qpos (2) | mat2euler(object xmat) | (object_velp - grip_velp) dt |
+//   object_velr dt | grip_velp dt | finger qvel dt (2)
+__device__ __forceinline__ void oq_mul(const double* a, const double* b, double* r) {
+  const double r0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], r1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  const double r2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], r3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3;
+}
+__device__ __forceinline__ void oq_mat(const double* q, double* R) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+__device__ __forceinline__ void oq_norm(double* q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  n = n < 1e-15 ? 1e-15 : n;
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+#define OMV(R, v, o) { o[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2]; o[1] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2]; o[2] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2]; }
+#define OCROSS(a, b, o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+__global__ void __launch_bounds__(128) openai_obs_kernel(const ModelT<float> m, const float* __restrict__ state, int n, int S, int block_body,
+                                                        int adr_l, int adr_r, int dof_l, int dof_r, float* __restrict__ obs) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float* qpos = state + (size_t)e * S;
+  const float* qvel = qpos + m.nq;
+  double xpos[HSRB_MAXBODY][3], xquat[HSRB_MAXBODY][4], velp[HSRB_MAXBODY][3], velr[HSRB_MAXBODY][3];
+  for (int k = 0; k < 3; k++) { xpos[0][k] = 0; velp[0][k] = 0; velr[0][k] = 0; }
+  xquat[0][0] = 1; xquat[0][1] = xquat[0][2] = xquat[0][3] = 0;
+  for (int b = 1; b < m.nbody; b++) {
+    const int p = m.body_parent[b], j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
+    if (nj == 1 && m.jnt_type[j0] == JNT_FREE) {
+      const int a = m.jnt_qposadr[j0], v = m.jnt_dofadr[j0];
+      double q[4] = {(double)qpos[a + 3], (double)qpos[a + 4], (double)qpos[a + 5], (double)qpos[a + 6]}, R[9];
+      oq_norm(q); oq_mat(q, R);
+      const double w[3] = {(double)qvel[v + 3], (double)qvel[v + 4], (double)qvel[v + 5]};
+      double wr[3];
+      OMV(R, w, wr);
+      for (int k = 0; k < 3; k++) { xpos[b][k] = (double)qpos[a + k]; velp[b][k] = (double)qvel[v + k]; velr[b][k] = wr[k]; }
+      for (int k = 0; k < 4; k++) xquat[b][k] = q[k];
+      continue;
+    }
+    double Rp[9], pos[3], quat[4], w[3], vel[3], t3[3], d3[3];
+    oq_mat(xquat[p], Rp);
+    const double bp[3] = {(double)m.body_pos[3 * b], (double)m.body_pos[3 * b + 1], (double)m.body_pos[3 * b + 2]};
+    const double bq[4] = {(double)m.body_quat[4 * b], (double)m.body_quat[4 * b + 1], (double)m.body_quat[4 * b + 2], (double)m.body_quat[4 * b + 3]};
+    OMV(Rp, bp, t3);
+    for (int k = 0; k < 3; k++) { pos[k] = xpos[p][k] + t3[k]; w[k] = velr[p][k]; d3[k] = pos[k] - xpos[p][k]; }
+    oq_mul(xquat[p], bq, quat);
+    OCROSS(velr[p], d3, t3);
+    for (int k = 0; k < 3; k++) vel[k] = velp[p][k] + t3[k];   // origin of b carried rigidly by its parent
+    for (int j = j0; j < j0 + nj; j++) {
+      double R[9], anchor[3], axis[3];
+      oq_mat(quat, R);
+      const double jp[3] = {(double)m.jnt_pos[3 * j], (double)m.jnt_pos[3 * j + 1], (double)m.jnt_pos[3 * j + 2]};
+      const double ja[3] = {(double)m.jnt_axis[3 * j], (double)m.jnt_axis[3 * j + 1], (double)m.jnt_axis[3 * j + 2]};
+      OMV(R, jp, t3);
+      for (int k = 0; k < 3; k++) anchor[k] = pos[k] + t3[k];
+      OMV(R, ja, axis);
+      const int a = m.jnt_qposadr[j], v = m.jnt_dofadr[j];
+      const double q = (double)qpos[a] - (double)m.qpos0[a], qd = (double)qvel[v];
+      if (m.jnt_type[j] == JNT_SLIDE) {
+        for (int k = 0; k < 3; k++) { pos[k] += axis[k] * q; vel[k] += axis[k] * qd; }
+      } else {
+        const double half = 0.5 * q, sh = sin(half);
+        const double dq[4] = {cos(half), sh * ja[0], sh * ja[1], sh * ja[2]};
+        oq_mul(quat, dq, quat);
+        oq_mat(quat, R);
+        OMV(R, jp, t3);
+        for (int k = 0; k < 3; k++) { pos[k] = anchor[k] - t3[k]; w[k] += axis[k] * qd; d3[k] = pos[k] - anchor[k]; }
+        const double aw[3] = {axis[0] * qd, axis[1] * qd, axis[2] * qd};
+        OCROSS(aw, d3, t3);
+        for (int k = 0; k < 3; k++) vel[k] += t3[k];
+      }
+    }
+    oq_norm(quat);
+    for (int k = 0; k < 3; k++) { xpos[b][k] = pos[k]; velp[b][k] = vel[k]; velr[b][k] = w[k]; }
+    for (int k = 0; k < 4; k++) xquat[b][k] = quat[k];
+  }
+  double gp[3] = {0, 0, 0}, gv[3] = {0, 0, 0};
+  for (int f = 0; f < 2; f++) {
+    const int b = m.finger_body[f];
+    double R[9], r[3], t3[3];
+    oq_mat(xquat[b], R);
+    const double fp[3] = {(double)m.finger_pos[3 * f], (double)m.finger_pos[3 * f + 1], (double)m.finger_pos[3 * f + 2]};
+    OMV(R, fp, r);
+    OCROSS(velr[b], r, t3);
+    for (int k = 0; k < 3; k++) { gp[k] += 0.5 * (xpos[b][k] + r[k]); gv[k] += 0.5 * (velp[b][k] + t3[k]); }
+  }
+  const double dt = (double)m.timestep;
+  double Rb[9];
+  oq_mat(xquat[block_body], Rb);
+  // mat2euler, /root/reference/hsr/env.py:256-272
+  const double cy = sqrt(Rb[8] * Rb[8] + Rb[5] * Rb[5]);
+  const bool cond = cy > 2.220446049250313e-16 * 4;
+  const double e2 = cond ? -atan2(Rb[1], Rb[0]) : -atan2(-Rb[3], Rb[4]);
+  const double e1 = -atan2(-Rb[2], cy);
+  const double e0 = cond ? -atan2(Rb[5], Rb[8]) : 0.0;
+  float* o = obs + (size_t)e * 25;
+  const double* op = xpos[block_body];
+  for (int k = 0; k < 3; k++) {
+    o[k] = (float)gp[k]; o[3 + k] = (float)op[k]; o[6 + k] = (float)(op[k] - gp[k]);
+    o[14 + k] = (float)((velp[block_body][k] - gv[k]) * dt); o[17 + k] = (float)(velr[block_body][k] * dt); o[20 + k] = (float)(gv[k] * dt);
+  }
+  o[9] = adr_l >= 0 ? qpos[adr_l] : 0.f; o[10] = adr_r >= 0 ? qpos[adr_r] : 0.f;
+  o[11] = (float)e0; o[12] = (float)e1; o[13] = (float)e2;
+  o[23] = dof_l >= 0 ? (float)((double)qvel[dof_l] * dt) : 0.f; o[24] = dof_r >= 0 ? (float)((double)qvel[dof_r] * dt) : 0.f;
+}
+#undef OMV
+#undef OCROSS
 
 __global__ void gather_state(const float* __restrict__ st, int n, int S, int off, int w, float* __restrict__ out) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -620,6 +751,22 @@ int hsrb_forward(hsrb_t* h, float* body_xpos, float* gripper_pos, void* stream) 
   KArgs a = base_args(h);
   a.mode = MODE_FORWARD; a.body_xpos = body_xpos; a.gripper = gripper_pos;
   return run(h, a, stream);
+}
+
+int hsrb_openai_obs(hsrb_t* h, int finger_qposadr_l, int finger_qposadr_r, int finger_dofadr_l, int finger_dofadr_r, float* obs25,
+                    void* stream) {
+  if (!h) return fail(-1, "null handle");
+  if (!obs25) return fail(-1, "obs25 is NULL");
+  const auto& m = h->hm.m;
+  if (m.nblock < 1) return fail(-3, "the 'openai' observation needs a block (hsr/env.py:58)");
+  if (m.nbody > HSRB_MAXBODY) return fail(-3, "more than %d bodies", HSRB_MAXBODY);
+  if (finger_qposadr_l >= m.nq || finger_qposadr_r >= m.nq || finger_dofadr_l >= m.nv || finger_dofadr_r >= m.nv)
+    return fail(-1, "finger joint address out of range");
+  CU(cudaSetDevice(h->device));
+  openai_obs_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->dm, h->d_state, h->n, h->S, m.block_body[0], finger_qposadr_l,
+                                                                        finger_qposadr_r, finger_dofadr_l, finger_dofadr_r, obs25);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int hsrb_compute_reward(hsrb_t* h, float* reward, uint8_t* success, void* stream) {

@@ -94,6 +94,7 @@ class BatchedHSREnv:
             raise NotImplementedError(f"obs_type={obs_type!r}: the default qpos|qvel observation (hsr/env.py:111-113) and "
                                       "'openai' (hsr/env.py:72-110) are implemented")
         self._obs_type = obs_type
+        self._finger_adr = None   # qpos / dof addresses of the two proximal finger joints (openai observation)
         self.model = load_model(xml_file)
         self.starts = dict(starts or {})
         self.goals_specs = list(goals) if goals else []
@@ -328,13 +329,20 @@ class BatchedHSREnv:
         from it on the device (hsr_env_b200/kin.py states the intent of the reference's dead branch)."""
         if self._obs_type != "openai":
             return state
-        from . import kin
-
         if not len(self.model.block_body):
             raise NotImplementedError("the 'openai' observation needs a block (hsr/env.py:58 `_block_name`)")
-        obs = kin.openai_observation(self.model, state[:, :self.nq], state[:, self.nq:], float(self.model.timestep),
-                                     int(self.model.block_body[0]))
-        return obs.to(torch.float32)
+        if self._finger_adr is None:
+            names = list(self.model.names.get("joint", []))
+            adr = []
+            for jn in ("hand_l_proximal_joint", "hand_r_proximal_joint"):
+                j = names.index(jn) if jn in names else -1
+                adr.append((int(self.model.jnt_qposadr[j]), int(self.model.jnt_dofadr[j])) if j >= 0 else (-1, -1))
+            self._finger_adr = adr
+        (ql, dl), (qr, dr) = self._finger_adr
+        obs = self._empty(self.n_envs, 25)
+        with torch.cuda.device(self.device):   # one kernel on the resident state (hsrb_api.cu openai_obs_kernel); kin.py is the test oracle
+            _lib.check(self._lib.hsrb_openai_obs(self._h, ql, qr, dl, dr, _lib.ptr(obs), self._stream()))
+        return obs
 
     def compute_reward(self) -> torch.Tensor:
         """float(all in_range) of the current state (north star name; hsr/env.py:126,133)."""

@@ -31,6 +31,7 @@ SIGNATURES = {
     "hsrb_get_state": (c_int, [c_void_p] + [c_void_p] * 5),
     "hsrb_set_state": (c_int, [c_void_p] + [c_void_p] * 5),
     "hsrb_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hsrb_openai_obs": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hsrb_compute_reward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsrb_debug_size": (c_int, [c_void_p]),
     "hsrb_debug_substep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -96,6 +96,16 @@ int hsrb_set_state(hsrb_t* h, const float* qpos, const float* qvel, const float*
  * body_xpos[N, nbody, 3]; gripper_pos[N,3] = mean of the two distal finger links (nullable). */
 int hsrb_forward(hsrb_t* h, float* body_xpos, float* gripper_pos, void* stream);
 
+/* HSREnv._get_observation, obs_type 'openai'                      env.py:72-110
+ * The 25-d Fetch-style observation from the resident state (forward kinematics with 6-D body velocities on the
+ * device): grip_pos | object_pos | object_pos - grip_pos | finger qpos (2) | mat2euler(object xmat) |
+ * (object_velp - grip_velp) dt | object_velr dt | grip_velp dt | finger qvel dt (2).  The reference branch is dead
+ * code in the snapshot; this is its intent as stated in hsr_env_b200/kin.py.  The finger
+ * addresses are the qpos / dof addresses of hand_l_proximal_joint and hand_r_proximal_joint, -1 when --use-dof
+ * removed the joint (zeros).  obs25[N, 25]. */
+int hsrb_openai_obs(hsrb_t* h, int finger_qposadr_l, int finger_qposadr_r, int finger_dofadr_l, int finger_dofadr_r,
+                    float* obs25, void* stream);
+
 /* compute_reward (named by the north star; absent from the snapshot, defined as float(all in_range) to
  * agree with env.py:126,133): reward[N] / success[N] of the CURRENT state, no stepping. */
 int hsrb_compute_reward(hsrb_t* h, float* reward, uint8_t* success, void* stream);

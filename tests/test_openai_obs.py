@@ -1,5 +1,6 @@
 """Row f1: the 'openai' observation.  Host-side torch kinematics (hsr_env_b200/kin.py) against the numpy
-oracle's kinematics and Jacobians on CPU; on the GPU, the observation's positions against the kernel's own forward pass."""
+oracle's kinematics and Jacobians on CPU; on the GPU, the observation kernel (hsrb_openai_obs) against that torch statement
+and against the action kernel's own forward pass."""
 import numpy as np
 import pytest
 
@@ -76,7 +77,31 @@ def test_openai_observation_against_the_kernel_forward_pass():
         lo = torch.tensor(env.model.act_ctrlrange[:, 0], dtype=torch.float32); hi = torch.tensor(env.model.act_ctrlrange[:, 1], dtype=torch.float32)
         obs, reward, done, info = env.step(lo + (hi - lo) * torch.rand(n, env.nu, generator=gen))
         assert obs.shape == (n, 25) and torch.isfinite(obs).all()
-        # positions of the torch kinematics = the CUDA kernel's forward pass (hsrb_forward)
+        # the observation kernel (hsrb_openai_obs) = the torch / fp64 statement of the observation (kin.py, checked against
+        # the numpy oracle above) on the same state: all 25 components, fp32 output rounding only
+        from hsr_env_b200 import kin
+
+        qpos, qvel, _, _ = env.get_state()
+        ref = kin.openai_observation(env.model, qpos, qvel, float(env.model.timestep), int(env.model.block_body[0]))
+        err = (obs.double() - ref).abs()
+        assert float(err.max()) <= 2e-6, float(err.max())
+        # and its positions = the action kernel's own forward pass (hsrb_forward)
         assert torch.allclose(obs[:, 0:3], env.gripper_pos(), atol=2e-6)
         assert torch.allclose(obs[:, 3:6], env.block_pos()[:, 0], atol=2e-6)
+    env.close()
+
+
+@pytest.mark.gpu
+def test_openai_observation_without_finger_joints():
+    """--use-dof slide_x slide_y: the finger joints are gone, their observation slots are zero (kin.py does the same)."""
+    from hsr_env_b200 import kin
+    from hsr_env_b200.env import BatchedHSREnv
+
+    env = BatchedHSREnv("c2_push.hsrb", None, obs_type="openai", n_envs=32, device="cuda:0", steps_per_action=10)
+    obs = env.reset()
+    obs, _, _, _ = env.step(torch.zeros(32, env.nu))
+    qpos, qvel, _, _ = env.get_state()
+    ref = kin.openai_observation(env.model, qpos, qvel, float(env.model.timestep), int(env.model.block_body[0]))
+    assert float((obs.double() - ref).abs().max()) <= 2e-6
+    assert float(obs[:, 9:11].abs().max()) == 0.0 and float(obs[:, 23:25].abs().max()) == 0.0
     env.close()
