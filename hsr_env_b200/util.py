@@ -1,5 +1,8 @@
 """CLI flags + env wrapper of the reference, kept verbatim, feeding the batched backend.
 
+NOTE: most of this file is the REFERENCE'S OWN CODE carried over as the interface schema (flag declarations, parser helper
+bodies); it is not original work of this repository and sits off the hot path.
+
 Mirrors /root/reference/hsr/util.py:16-81 (``add_env_args``, ``add_wrapper_args``, ``xml_setter``,
 ``env_wrapper``) and /root/reference/rl_utils/argparse.py:10-73 (``hierarchical_parse_args``, ``make_box``,
 ``parse_space``, ``parse_vector``).  Where the reference writes a mutated temp MJCF for MuJoCo to load

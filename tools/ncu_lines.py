@@ -25,7 +25,11 @@ for r in rows:
         continue
     if r[0] != '':
         key = (cur, int(r[0]))
-        agg[key][1] += int(r[7]); agg[key][2] += int(r[6]); agg[key][3] += int(r[8]); agg[key][4] = r[1].strip()[:110]
+        try:
+            agg[key][1] += int(r[7]); agg[key][2] += int(r[6]); agg[key][3] += int(r[8])
+        except ValueError:
+            pass
+        agg[key][4] = r[1].strip()[:110]
     else:
         agg[key][0] += 1
 tot_e = sum(v[1] for v in agg.values()); tot_s = sum(v[2] for v in agg.values())
