@@ -1489,13 +1489,18 @@ HSR_HDC T linesearch(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int
 }
 
 // Newton solver on the primal convex cost; on exit w.qacc, w.force (and w.tmpv = J^T force) are final.
+// The Newton solver in three pieces, so that a kernel whose warps lock-step through the passes (hsrb_step_lock_kernel: one
+// block vote per pass keeps every warp of the block in the same code region) can drive the loop itself:
+//   newton_begin (warm start, cost of the starting point) -> while (newton_pass) -> newton_end (J^T f, counters).
+template <typename T> struct NewtonState { T cost, scale; int it; };
 template <typename T, typename Grp>
-HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc) {
+HSR_HDC bool newton_begin(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc, NewtonState<T>& ns) {
   int nv = m.nv;
+  ns.it = 0; ns.cost = 0; ns.scale = T(1) / (m.meaninertia * T(nv > 1 ? nv : 1));
   if (nefc == 0) {
     for (int i = g.lane; i < nv; i += Grp::G) { w.qacc[i] = w.qacc_smooth[i]; w.tmpv[i] = 0; }
     g.sync();
-    return;
+    return false;
   }
   // warm start: lower cost of qacc_warmstart / qacc_smooth
   T gw = residuals(m, w, g, w.warm, nefc);
@@ -1510,11 +1515,16 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
   g.sync();
   T gauss = use_warm ? residuals(m, w, g, w.qacc, nefc) : gs;
   g.sync();
-  T cost = constraint_update(m, w, g, nlimit, ncon, true) + gauss;
+  ns.cost = constraint_update(m, w, g, nlimit, ncon, true) + gauss;
   g.sync();
-  T scale = T(1) / (m.meaninertia * T(nv > 1 ? nv : 1));
-  int it = 0;
-  while (true) {
+  return true;
+}
+// one pass: gradient, convergence tests, Hessian, Newton direction, line search, update; false = the solver has stopped
+template <typename T, typename Grp>
+HSR_HDC bool newton_pass(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc, NewtonState<T>& ns) {
+  const int nv = m.nv;
+  const T scale = ns.scale;
+  {
     // gradient (dofs across lanes) and Hessian H = M + J^T W (lower triangle entries across lanes)
     T gn = 0;
     for (int i = g.lane; i < nv; i += Grp::G) {
@@ -1523,8 +1533,8 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
       w.grad[i] = s; gn += s * s;
     }
     gn = sqrt(g.sum(gn));
-    if (it > 0 && scale * gn < m.tolerance) break;
-    if (it >= m.iterations) break;
+    if (ns.it > 0 && scale * gn < m.tolerance) return false;
+    if (ns.it >= m.iterations) return false;
     int ntri = nv * (nv + 1) / 2;
     for (int e = g.lane; e < ntri; e += Grp::G) {
       int a = 0, rem = e;
@@ -1552,7 +1562,7 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
     for (int i = g.lane; i < nv; i += Grp::G) { sn += w.search[i] * w.search[i]; dec -= w.grad[i] * w.search[i]; }
     sn = sqrt(g.sum(sn));
     dec = g.sum(dec);  // Newton decrement^2 = grad^T H^-1 grad
-    if (sn < Lim<T>::minval()) break;
+    if (sn < Lim<T>::minval()) return false;
     for (int i = g.lane; i < nv; i += Grp::G) {
       T s = 0;
       for (int d = 0; d < nv; d++) s += w.M[i * nv + d] * w.search[d];
@@ -1566,7 +1576,7 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
     g.sync();
     T gtol = m.tolerance * m.ls_tolerance * sn / scale;
     T alpha = linesearch(m, w, g, nlimit, ncon, gtol);
-    if (alpha == 0) break;
+    if (alpha == 0) return false;
     T gsum = 0;
     for (int i = g.lane; i < nv; i += Grp::G) {
       w.qacc[i] += alpha * w.search[i]; w.Ma[i] += alpha * w.Mv[i];
@@ -1575,24 +1585,36 @@ HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit
     for (int r = g.lane; r < nefc; r += Grp::G) w.jar[r] += alpha * w.jv[r];
     gsum = g.sum(gsum);
     g.sync();
-    T old = cost;
-    cost = constraint_update(m, w, g, nlimit, ncon, true) + gsum;
+    T old = ns.cost;
+    ns.cost = constraint_update(m, w, g, nlimit, ncon, true) + gsum;
     g.sync();
-    it++;
+    ns.it++;
     // improvement of this step.  The reference tests old - cost; in fp32 that difference of two large numbers
     // is rounding noise near convergence, so the quadratic-model prediction alpha (1 - alpha/2) grad^T H^-1 grad
     // is used instead (equal to old - cost to second order, free of cancellation); the measured difference is
     // kept only where the model does not apply (alpha >= 2).
-    T improvement = alpha < T(2) ? alpha * (T(1) - T(0.5) * alpha) * dec : old - cost;
-    if (scale * improvement < m.tolerance) break;
+    T improvement = alpha < T(2) ? alpha * (T(1) - T(0.5) * alpha) * dec : old - ns.cost;
+    if (scale * improvement < m.tolerance) return false;
   }
+  return true;
+}
+template <typename T, typename Grp>
+HSR_HDC void newton_end(const ModelT<T>& m, WS<T>& w, const Grp& g, int nefc, const NewtonState<T>& ns) {
+  const int nv = m.nv;
   for (int i = g.lane; i < nv; i += Grp::G) {
     T s = 0;
     for (int r = 0; r < nefc; r++) s += w.J[r * nv + i] * w.force[r];
     w.tmpv[i] = s;
   }
-  if (g.lane == 0) w.wi[WI_ITER] += it;
+  if (g.lane == 0) w.wi[WI_ITER] += ns.it;
   g.sync();
+}
+template <typename T, typename Grp>
+HSR_HDC void solve_newton(const ModelT<T>& m, WS<T>& w, const Grp& g, int nlimit, int ncon, int nefc) {
+  NewtonState<T> ns;
+  if (!newton_begin(m, w, g, nlimit, ncon, nefc, ns)) return;
+  while (newton_pass(m, w, g, nlimit, ncon, nefc, ns)) {}
+  newton_end(m, w, g, nefc, ns);
 }
 
 // ------------------------------------------------------------------------------------------------ B.8 Euler

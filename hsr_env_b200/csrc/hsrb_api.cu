@@ -219,6 +219,7 @@ int configure_wpe(hsrb* h) {
   const int need = (h->n + wpb - 1) / wpb;
   const int cap = h->wpe_bps * h->num_sm;
   h->wpe_grid = need < cap ? need : cap;
+  if (wpb > 1 && h->wpe_grid < cap && 2 * h->wpe_grid > cap) h->wpe_grid = cap;   // 4096 envs: 148 blocks of 27-28 instead of 147 of 28 + an idle SM
   if (const char* o = getenv("HSRB_WPE_GRID")) { int v = atoi(o); if (v >= 1 && v < h->wpe_grid) h->wpe_grid = v; }   // experiments
   h->wpe_configured = true;
   return 0;

@@ -186,21 +186,35 @@ __global__ void __launch_bounds__(32 * HSRB_LOCK_MAXWARPS) hsrb_step_lock_kernel
     for (int sb = 0; sb < a.nsub; sb++) {
       if (__syncthreads_and(finished)) break;
       int nlimit = 0, nrow = 0, ncon = 0, it0 = 0, ls0 = 0;
+      // PH: block barriers between ALL phases (not only around the job service), PL: one block vote per Newton pass - the
+      // warps of the block then run the same code region at the same time (the instruction stream of a substep of this
+      // kernel is several hundred KB; free-running warps spent half of their stall samples waiting for instructions).
+      // a.opts bit 1 / bit 2 switch them off (experiments)
+      const bool PH = !(a.opts & 2u), PL = !(a.opts & 4u);
       if (!finished) {
         HSR_PHASE_START(w, g);
         kinematics_trig(m, w, g);
         if (g.lane == 0) kinematics_lane0(m, w);
         g.sync();
         HSR_PHASE(w, g, PH_KIN);
+      }
+      if (PH) __syncthreads();
+      if (!finished) {
         cdof_geoms(m, w, g);
         g.sync();
         mass_matrix(m, w, g);
         g.sync();
         HSR_PHASE(w, g, PH_CRB);
+      }
+      if (PH) __syncthreads();
+      if (!finished) {
         if (g.lane == 0) smooth_lane0(m, w);
         g.sync();
         smooth_solve(m, w, g);
         HSR_PHASE(w, g, PH_SMOOTH);
+      }
+      if (PH) __syncthreads();
+      if (!finished) {
         for (int j = 0; j < m.njnt; j++) {
           if (!m.jnt_limited[j] || m.jnt_type[j] == JNT_FREE) continue;
           const float q = w.qpos[m.jnt_qposadr[j]];
@@ -259,13 +273,29 @@ __global__ void __launch_bounds__(32 * HSRB_LOCK_MAXWARPS) hsrb_step_lock_kernel
         ncon = collision_assemble(m, w, g, nrow);
         g.sync();
         HSR_PHASE(w, g, PH_COLLIDE);
+      }
+      if (PH) __syncthreads();
+      if (!finished) {
         make_constraint(m, w, g, nlimit, ncon);
         it0 = w.wi[WI_ITER]; ls0 = w.wi[WI_LSEVAL];
         g.sync();
         if (g.lane == 0) { w.wi[WI_NCON] = ncon; w.wi[WI_NEFC] = nrow; w.wi[WI_NLIMIT] = nlimit; }
         g.sync();
         HSR_PHASE(w, g, PH_ROWS);
+      }
+      if (PH) __syncthreads();
+      if (PL) {
+        NewtonState<float> ns;
+        bool act = !finished && newton_begin(m, w, g, nlimit, ncon, nrow, ns);
+        const bool solved = act;
+        while (__syncthreads_or(act)) {
+          if (act) act = newton_pass(m, w, g, nlimit, ncon, nrow, ns);
+        }
+        if (solved) newton_end(m, w, g, nrow, ns);
+      } else if (!finished) {
         solve_newton(m, w, g, nlimit, ncon, nrow);
+      }
+      if (!finished) {
         HSR_PHASE(w, g, PH_SOLVE);
         if (g.lane == 0) {
           w.wi[WI_SUMCON] += ncon; w.wi[WI_SUMEFC] += nrow;
