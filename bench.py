@@ -394,8 +394,8 @@ def run_gpu(args):
     b_alg = 4 * ((nq + 2 * nv + nu + 3 + 2) + (nq + 2 * nv + (nq + nv) + 4))
     achieved_gbs = b_alg * n / r["kernel_s"] / 1e9
     traffic = None
-    tp = ROOT / "profiles" / "r01_traffic.json"
-    if tp.exists() and n == 4096 and info["kernel"] == "fast":
+    tp = ROOT / "profiles" / "r02_traffic.json"
+    if tp.exists() and n == 4096 and info["kernel"] == "wpe":
         traffic = json.loads(tp.read_text())["dram_bytes_per_launch"]
     clocks = clk.summary()
     secs_max = r["secs"]
@@ -421,7 +421,7 @@ def run_gpu(args):
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                      "traffic": traffic,
                      "traffic_source": ("static: dram__bytes_read+write of one ncu --set full capture of this kernel and batch, "
-                                        "profiles/r01_traffic.json; not measured in this run") if traffic is not None else None,
+                                        "profiles/r02_traffic.json; not measured in this run") if traffic is not None else None,
                      "peak_source": "FP32 FMA-loop peak measured in this run (hsrb_measure_fp32_peak: 8 FMA chains x 1024 threads x 2 blocks per SM)",
                      "kernel": kname, "kernel_ms_per_launch": 1e3 * r["kernel_s"],
                      "algorithmic_flops_per_substep": f_alg,
