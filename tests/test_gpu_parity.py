@@ -459,3 +459,40 @@ def test_wpe_work_sorted_launch_order_does_not_change_results(monkeypatch):
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
     assert int(sum(int(x.sum()) for x in outs[0][3::4])) == 0
+
+
+def test_million_env_shard_is_bit_exact_against_small_batches():
+    """configs[3]: rank 3 of 8 of the 2^20-environment job (131072 environments, global ids 393216 ...) - many waves per
+    block, work-sorted launch order - gives, for three actions with resets in between, the same bits as 4096-environment
+    handles created on slices of those ids: an environment's trajectory depends on its global id only, not on the batch,
+    the rank count, the wave it runs in or the launch order."""
+    from hsr_env_b200.env import BatchedHSREnv
+    from hsr_env_b200.spaces import Box
+    from hsr_env_b200.util import GoalSpec
+    from scenarios import BLOCK_HI, BLOCK_LO, GOAL_HI, GOAL_LO
+
+    goals = [GoalSpec(Box(BLOCK_LO, BLOCK_HI), Box(GOAL_LO, GOAL_HI), .05)]
+    n_rank, rank = (1 << 20) // 8, 3
+    off = rank * n_rank
+    gen = torch.Generator().manual_seed(11)
+    acts = torch.rand(3, n_rank, 2, generator=gen) * 2 - 1
+
+    def run(n, o, a):
+        env = BatchedHSREnv("c2_push.hsrb", goals, n_envs=n, device="cuda:0", seed=9, env_id_offset=o, kernel="wpe")
+        env.reset()
+        res = []
+        for k in range(3):
+            obs, reward, done, info = env.step(a[k])
+            res.append((obs.cpu().numpy(), done.cpu().numpy(), info["substeps_taken"].cpu().numpy()))
+            env.reset(mask=done)
+        bad = int(info["bad_state"].sum())
+        env.close()
+        return res, bad
+
+    big, bad = run(n_rank, off, acts)
+    assert bad == 0
+    for lo in (0, 61440, n_rank - 4096):   # first, a middle and the last slice of the shard
+        small, _ = run(4096, off + lo, acts[:, lo:lo + 4096].contiguous())
+        for k in range(3):
+            for x, y in zip(big[k], small[k]):
+                assert np.array_equal(x[lo:lo + 4096], y), (lo, k)
