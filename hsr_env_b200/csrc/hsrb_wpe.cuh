@@ -27,7 +27,7 @@
 #define WPE_MAXBG 2                        // geoms riding on the block
 #define WPE_MAXGEOM 24                     // capacities of the fixed shared-memory layout (c2_push: 18 geoms, 21 pairs)
 #define WPE_MAXPAIR 24
-#define WPE_ENVJOBS 8                      // phase-locked variant: convex-convex jobs an environment can queue per substep
+#define WPE_ENVJOBS 7                      // phase-locked variant: convex-convex jobs an environment can queue per substep
 #ifndef WPE_MAXWARPS
 #define WPE_MAXWARPS 28
 #endif
@@ -59,7 +59,8 @@ struct alignas(16) Slice {   // per-warp (= per-environment) slice
   float qs[8], as[8], x[8], qfc[8], srch[8];
   float con_dist[WPE_MAXCON], con_pos[WPE_MAXCON * 3], con_frame[WPE_MAXCON * 9];
   int con_pair[WPE_MAXCON], con_adr[WPE_MAXCON], wi[4];
-  float jres[WPE_ENVJOBS * 14];                                // phase-locked variant: results of this environment's convex-convex jobs (hit, dist, pos, frame)
+  int acc[8];                                                  // per-action counters of the environment (lane 0): registers would stay live across every call
+  float jres[WPE_ENVJOBS * 14 + 2];                                // phase-locked variant: results of this environment's convex-convex jobs (hit, dist, pos, frame)
   float J[WPE_SLOTS * 8];                                       // 32-byte Jacobian rows
   float Dr[WPE_SLOTS], aref[WPE_SLOTS], rsc[WPE_SLOTS], jar[WPE_SLOTS], jv[WPE_SLOTS], f[WPE_SLOTS], wrow[WPE_SLOTS];   // per row slot (rsc: mu on row 0, friction[j-1] on row j)
   float PQ[16 * WPE_GROUPS], wpq[2 * WPE_GROUPS + 4], L[64];
@@ -75,6 +76,10 @@ struct alignas(16) Queue {
   int jobs[WPE_MAXWARPS * WPE_ENVJOBS];       // (owner warp << 16) | (slot << 8) | pair; team k owns a contiguous share
 };
 
+static_assert(offsetof(Slice, J) % 16 == 0 && offsetof(Slice, PQ) % 16 == 0 && offsetof(Slice, L) % 16 == 0 && offsetof(Slice, qpos) % 16 == 0 &&
+              offsetof(Slice, qvel) % 16 == 0 && offsetof(Slice, qs) % 16 == 0 && offsetof(Slice, x) % 16 == 0 && offsetof(Slice, srch) % 16 == 0 &&
+              offsetof(Slice, warm) % 16 == 0 && offsetof(Slice, as) % 16 == 0 && sizeof(Slice) % 16 == 0,
+              "128-bit shared-memory accesses (push::ld8 / st8) need 16-byte aligned fields");
 __host__ __device__ inline size_t slice_bytes() { return sizeof(Slice); }
 // block-shared tail after the slices: the tables, the job queue, then the hull vertices as float4
 __host__ __device__ inline size_t shared_tail(const ModelT<float>& m) { return sizeof(Tab) + sizeof(Queue) + (size_t)m.nvert * 16 + 16; }
@@ -131,10 +136,13 @@ __device__ __forceinline__ const double* geom_mat(const Tab& t, const Slice& s, 
   return t.gmove[gi] == 2 ? s.bmat + 9 * (gi - gb0) : t.gmatw + 9 * gi;
 }
 
+#ifndef WPE_SUPPORT_ATTR
+#define WPE_SUPPORT_ATTR __forceinline__   // inlined at its two call sites in mpr: no call-site spills on the refinement chain (+1-3 %)
+#endif
 // support point of geom gi along d (world frame); hull scan in fp32 over the 32 lanes, everything else in double
 // (same arithmetic as hsr::support_d)
 // (s: the slice of the environment the geom belongs to)
-__device__ __noinline__ V3d support(const Tab& t, const Slice& s, const float* verts4, int gi, int gb0, V3d d) {
+__device__ WPE_SUPPORT_ATTR V3d support(const Tab& t, const Slice& s, const float* verts4, int gi, int gb0, V3d d) {
   WPE_CK_DECL;
   const double* R = geom_mat(t, s, gi, gb0);
   const V3d dl = multv(R, d);
@@ -460,11 +468,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       if (lane < 3) s.xb[lane] = 0;
       if (lane < 9) s.Rb[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
     }
-    int n_iter = 0, n_ls = 0, sumcon = 0, sumefc = 0, kflop = 0, flags = 0, narrow_tot = 0;
+    int flags = 0;
+    enum { A_ITER = 0, A_LS, A_CON, A_EFC, A_KFLOP, A_NARROW, A_HIT };   // s.acc slots
+    if (lane < 8) s.acc[lane] = 0;
 #if defined(WPE_CHAIN_CLOCKS)
     const long long ck_env0 = clock64();
 #endif
-    int nhit_cc = 0;   // convex-convex contacts over the action (full portal refinements: the long narrowphase jobs)
     bool success = false;
     int taken = 0;
     bool finished = !valid || a.nsub <= 0;
@@ -684,7 +693,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
             const float* r = s.jres + 14 * kc;
             kc++;
             if (r[0] != 0.f) {
-              nhit_cc++;
+              if (lane == 0) s.acc[A_HIT]++;   // convex-convex contacts over the action (full portal refinements: the long jobs)
               if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
               else {
                 if (lane == 0) s.con_pair[ncon] = pk;
@@ -713,7 +722,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
               hitc = wpe::mpr(t, s, s, verts4, ga, gb, gb0, (double)m.mpr_tolerance, m.mpr_iterations, use_sep ? s.sep + 4 * pk : nullptr);
             }
             if (hitc) {
-              if (func == NP_CONVEX_CONVEX) nhit_cc++;
+              if (func == NP_CONVEX_CONVEX && lane == 0) s.acc[A_HIT]++;
               if (ncon >= WPE_MAXCON) flags |= FLAG_CON_OVERFLOW;
               else {
                 if (lane == 0) {
@@ -748,11 +757,10 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           }
         }
       }
-      narrow_tot += narrow;
       __syncwarp();
       ngrp = nlimit + ncon;
       nslot = 6 * ngrp;
-      sumcon += ncon; sumefc += nefc;
+      if (lane == 0) { s.acc[A_NARROW] += narrow; s.acc[A_CON] += ncon; s.acc[A_EFC] += nefc; }
 
       WPE_CK_RESET();
       // ---------------------------------------------------------------- smooth forces (closed form, B.6): dof lanes
@@ -1206,8 +1214,10 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       WPE_PH(PH_SOLVE);
       if (!finished) {
       WPE_CK_RESET();
-      n_iter += it; n_ls += ls_used;
-      kflop += algorithmic_flops(m, false, ncon, nefc, it, ls_used, npflop);   // slides + free box: M is constant
+      if (lane == 0) {
+        s.acc[A_ITER] += it; s.acc[A_LS] += ls_used;
+        s.acc[A_KFLOP] += algorithmic_flops(m, false, ncon, nefc, it, ls_used, npflop);   // slides + free box: M is constant
+      }
 
       // ---------------------------------------------------------------- goal test on the poses of this forward pass
       bool reached = false;
@@ -1279,15 +1289,15 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
 #if defined(WPE_CHAIN_CLOCKS)
         if (a.work) a.work[env] = (int)((clock64() - ck_env0) >> 10);   // measured: k-cycles of this environment's action
 #else
-        if (a.work) a.work[env] = 20 * taken + 7 * n_iter + 30 * nhit_cc + sumcon;
+        if (a.work) a.work[env] = 20 * taken + 7 * s.acc[A_ITER] + 30 * s.acc[A_HIT] + s.acc[A_CON];
 #endif
         atomicAdd(a.stats + ST_SUBSTEPS, (unsigned long long)taken);
-        atomicAdd(a.stats + ST_ITERS, (unsigned long long)n_iter);
-        atomicAdd(a.stats + ST_NARROW, (unsigned long long)narrow_tot);
-        atomicAdd(a.stats + ST_LSEVAL, (unsigned long long)n_ls);
-        atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)sumcon);
-        atomicAdd(a.stats + ST_ROWS, (unsigned long long)sumefc);
-        atomicAdd(a.stats + ST_FLOPS, (unsigned long long)kflop);
+        atomicAdd(a.stats + ST_ITERS, (unsigned long long)s.acc[A_ITER]);
+        atomicAdd(a.stats + ST_NARROW, (unsigned long long)s.acc[A_NARROW]);
+        atomicAdd(a.stats + ST_LSEVAL, (unsigned long long)s.acc[A_LS]);
+        atomicAdd(a.stats + ST_CONTACTS, (unsigned long long)s.acc[A_CON]);
+        atomicAdd(a.stats + ST_ROWS, (unsigned long long)s.acc[A_EFC]);
+        atomicAdd(a.stats + ST_FLOPS, (unsigned long long)s.acc[A_KFLOP]);
         if (flags) atomicAdd(a.stats + ST_BAD, 1ull);
       }
       __syncwarp();
