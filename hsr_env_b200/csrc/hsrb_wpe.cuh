@@ -197,7 +197,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
     V3d v0 = ld3(o.gpos + 3 * g1) - ld3(o.gpos + 3 * g2);
     if (fabs(v0.x) < eps && fabs(v0.y) < eps && fabs(v0.z) < eps) v0.x += eps * 10;
     V3d d;
-    if (sep && sep[3] == 1.f) {
+    if (sep && (sep[3] == 1.f || sep[3] < 0.f)) {
       state = S_CACHE;
       d = normalized(mk<double>((double)sep[0], (double)sep[1], (double)sep[2]));
     } else {
@@ -234,7 +234,10 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
     double dt = dot(v4, d);
     bool enter_refine = false;
     if (state == S_CACHE) {
-      if (dt < 0 && !is_zero(dt)) return false;            // the cached direction still separates the pair
+      if (dt < 0 && !is_zero(dt)) {                        // the cached direction still separates the pair, by -dt
+        if (lane == 0) sep[3] = (float)(dt * 0.999);       // remaining gap along it (negative flag = valid direction with a gap budget)
+        return false;
+      }
       if (lane == 0) sep[3] = 0.f;
       state = S_V1;
       d = normalized(-v0);
@@ -242,7 +245,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
     }
     if (state <= S_DISCOVER) {
       if (is_zero(dt) || dt < 0) {                         // origin outside the support plane: disjoint (or touching)
-        if (dt < 0 && !is_zero(dt) && sep && lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = 1.f; }
+        if (dt < 0 && !is_zero(dt) && sep && lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = (float)(dt * 0.999); }
         return false;
       }
     }
@@ -296,7 +299,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
     }
     if (state == S_REFINE && !enter_refine) {
       if (!(is_zero(dt) || dt > 0)) {                      // the new support point does not pass the origin: disjoint
-        if (sep && lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = 1.f; }
+        if (sep && lane == 0) { sep[0] = (float)d.x; sep[1] = (float)d.y; sep[2] = (float)d.z; sep[3] = (float)(dt * 0.999); }
         return false;
       }
     }
@@ -420,6 +423,12 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
   for (int i = m.ngeom - 1; i >= 0; i--) if (t.gmove[i] == 2) gb0 = i;
   const float Mi = li < NV ? fi.Mdiag[li] : 1.0f, dampi = li < NV ? fi.damp[li] : 0.f;
   const bool use_sep = !(a.opts & 1u);
+  const bool use_gap = use_sep && !(a.opts & 0x10000u);   // opts bit 16: no gap budget (every cached direction is re-checked every substep)
+  float blk_radius = 0.f;   // farthest point of the block's geoms from its body origin
+  for (int i = gb0; i < m.ngeom; i++) {
+    const double* o3 = t.gbase + 3 * i;
+    blk_radius = fmaxf(blk_radius, (float)sqrt(o3[0] * o3[0] + o3[1] * o3[1] + o3[2] * o3[2]) * 1.001f + t.geom_rbound[i]);
+  }
   // teams of the phase-locked variant: opts bits 4..7 = number of teams (0 -> 1); the warps of a team are contiguous
   int nteam = LOCK ? (int)((a.opts >> 4) & 15u) : 1;
   if (nteam < 1 || nteam > WPE_MAXTEAMS || wpb % nteam != 0) nteam = 1;
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
 #if defined(HSRB_PHASE_CLOCKS)
       if (LOCK && threadIdx.x == 0) tlast = clock64();
 #endif
-      int nlimit = 0, ncon = 0, nefc = 0, narrow = 0, npflop = 0, ngrp = 0, nslot = 0, gdim = 0;
+      int nlimit = 0, ncon = 0, nefc = 0, narrow = 0, npflop = 0, ngrp = 0, nslot = 0, gdim = 0, nskip = 0;
       unsigned bits = 0;                // candidate pairs of this environment that passed the cull
       int it = 0, ls_used = 0;
       WPE_CK_DECL;
@@ -583,7 +592,23 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
             hit = hit && fabsf(dp.x) <= ha[0] + hb[0] && fabsf(dp.y) <= ha[1] + hb[1] && fabsf(dp.z) <= ha[2] + hb[2];
           }
         }
-        bits = __ballot_sync(FULL, hit);
+        // Temporal coherence, exact: a convex-convex pair whose cached separating direction had a gap g after its last
+        // support evaluation is still separated along that direction while g exceeds the displacement any point of the two
+        // bodies can have made since (robot: a translation of dt |v|; block: dt |v| + dt |w| r); such a pair needs no
+        // support evaluation at all - the query could only answer "no contact".  The flag of the cache holds -g.
+        bool skip = false;
+        if (use_gap && k < m.npair && t.pair_func[k] == NP_CONVEX_CONVEX) {
+          float f = s.sep[4 * k + 3];
+          if (f < 0.f) {
+            const float moved = dt * 1.001f * (fabsf(s.qvel[0]) + fabsf(s.qvel[1]) + fabsf(s.qvel[2]) + fabsf(s.qvel[3]) + fabsf(s.qvel[4]) +
+                                               (fabsf(s.qvel[5]) + fabsf(s.qvel[6]) + fabsf(s.qvel[7])) * blk_radius) + 5e-8f;
+            f += moved;
+            if (f < -1e-6f) skip = hit; else f = 1.f;   // budget used up: the next query re-measures the gap with one support evaluation
+            s.sep[4 * k + 3] = f;
+          }
+        }
+        bits = __ballot_sync(FULL, hit && !skip);
+        nskip = __popc(__ballot_sync(FULL, skip));
       }
       WPE_CK(1);
       if (LOCK && lane == 0) {
@@ -597,7 +622,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
           bb &= bb - 1;
           if (t.pair_func[pk] != NP_CONVEX_CONVEX) continue;
           if (kc < WPE_ENVJOBS) {
-            const bool quick = use_sep && s.sep[4 * pk + 3] == 1.f;
+            const bool quick = use_sep && (s.sep[4 * pk + 3] == 1.f || s.sep[4 * pk + 3] < 0.f);
             const int code = (wib << 16) | (kc << 8) | pk;
             if (quick) qjobs[qcap - 1 - atomicAdd(&qcnt[1], 1)] = code;
             else qjobs[atomicAdd(&qcnt[0], 1)] = code;
@@ -760,6 +785,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
       __syncwarp();
       ngrp = nlimit + ncon;
       nslot = 6 * ngrp;
+      narrow += nskip; npflop += 5000 * nskip;   // pairs settled by the gap budget still count as the reference's narrowphase work
       if (lane == 0) { s.acc[A_NARROW] += narrow; s.acc[A_CON] += ncon; s.acc[A_EFC] += nefc; }
 
       WPE_CK_RESET();

@@ -496,3 +496,34 @@ def test_million_env_shard_is_bit_exact_against_small_batches():
         for k in range(3):
             for x, y in zip(big[k], small[k]):
                 assert np.array_equal(x[lo:lo + 4096], y), (lo, k)
+
+
+def test_wpe_gap_budget_is_exact(monkeypatch):
+    """Temporal coherence of the convex-convex queries: a pair whose cached separating direction still has a gap larger than
+    the displacement of the two bodies since it was measured is not evaluated at all.  That is a proof that the query
+    would answer "no contact", not an approximation: four actions (1200 substeps, resets in between) with the budget on
+    and off (HSRB_OPTS bit 16) give the same bits."""
+    from hsr_env_b200.env import BatchedHSREnv
+    from hsr_env_b200.spaces import Box
+    from hsr_env_b200.util import GoalSpec
+    from scenarios import BLOCK_HI, BLOCK_LO, GOAL_HI, GOAL_LO
+
+    goals = [GoalSpec(Box(BLOCK_LO, BLOCK_HI), Box(GOAL_LO, GOAL_HI), .05)]
+    n = 4096
+    acts = torch.rand(4, n, 2, generator=torch.Generator().manual_seed(13)) * 2 - 1
+    outs = []
+    for opts in ("0x10020", "0x20"):   # bits 4..7: two teams (the default)
+        monkeypatch.setenv("HSRB_OPTS", opts)
+        env = BatchedHSREnv("c2_push.hsrb", goals, n_envs=n, device="cuda:0", seed=6, kernel="wpe")
+        env.reset()
+        res = []
+        for k in range(4):
+            obs, reward, done, info = env.step(acts[k])
+            res += [obs.cpu().numpy(), done.cpu().numpy(), info["substeps_taken"].cpu().numpy(), info["bad_state"].cpu().numpy()]
+            env.reset(mask=done)
+        st = env.stats()
+        outs.append((res, st["contacts"], st["narrowphase"], st["flops"]))
+        env.close()
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(a, b)
+    assert outs[0][1:] == outs[1][1:]   # same contacts, same (algorithmic) narrowphase count and flops
