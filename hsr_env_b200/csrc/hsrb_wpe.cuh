@@ -636,7 +636,10 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         wpe::team_sync(team, tthreads);
         WPE_PH(PH_CRB);
         // ---- every warp of the block (finished ones included) serves jobs: the owner's poses, this warp's portal scratch
+        // (a team without jobs in this substep - the usual case for light environments since the gap budget - skips the
+        //  service and its closing barrier: the counters are not written again before the next two team barriers)
         const int nlong = qcnt[0], njobs = nlong + qcnt[1];
+        if (njobs > 0 || (a.opts & 0x20000u)) {   // opts bit 17: always run the service and its barrier (experiments)
 #pragma unroll 1
         while (true) {
           int j = 0;
@@ -672,6 +675,7 @@ __global__ void __launch_bounds__(32 * WPE_MAXWARPS, 1) hsrb_wpe_kernel_t(const 
         wpe::team_sync(team, tthreads);
         WPE_PH(PH_COLLIDE);
         if (wib == team * wpt && lane < 3) qcnt[lane] = 0;   // empty again; the next jobs are queued after the solver's barrier
+        }
       }
       if (!finished) {
       {
