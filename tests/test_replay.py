@@ -100,3 +100,31 @@ def test_fed_by_the_batched_env_on_the_device():
     newest = rb[-n:0]
     assert torch.equal(newest[3], obs)                 # the last batch written is the newest n items
     env.close()
+
+
+def _replay_golden(device):
+    """Replays tests/golden/replay.npz (outputs of the reference's own ReplayBuffer, tests/golden/make_replay_golden.py)."""
+    from hsr_env_b200.replay import ReplayBuffer
+
+    g = np.load(Path(__file__).parent / "golden" / "replay.npz")
+    buf = ReplayBuffer(maxlen=64, device=device)
+    for s, k in enumerate(g["sizes"]):
+        buf.extend([torch.tensor(g[f"in{s}_{j}"], device=device) for j in range(3)])
+        assert [buf.pos, int(buf.full), len(buf)] == g[f"pos{s}"].tolist()
+        for j, t in enumerate(buf.array()):
+            assert np.array_equal(t.cpu().numpy(), g[f"all{s}_{j}"])
+        idx = g[f"idx{s}"]
+        for j, t in enumerate(buf[torch.tensor(idx, device=device)]):
+            assert np.array_equal(t.cpu().numpy(), g[f"get{s}_{j}"])
+        win = np.array([np.arange(i, i + 5) for i in idx])
+        for j, t in enumerate(buf[torch.tensor(win, device=device)]):
+            assert np.array_equal(t.cpu().numpy(), g[f"win{s}_{j}"])
+
+
+def test_golden_outputs_of_the_reference_buffer_cpu():
+    _replay_golden("cpu")
+
+
+@pytest.mark.gpu
+def test_golden_outputs_of_the_reference_buffer_on_the_device():
+    _replay_golden("cuda:0")
