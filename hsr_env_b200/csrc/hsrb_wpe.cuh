@@ -193,6 +193,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
   enum { S_CACHE = 0, S_V1, S_V2, S_DISCOVER, S_REFINE, S_PENETRATE };
   const double eps = DBL_EPSILON;
   int state = S_V1;
+  V3d dcur;   // the current direction (loop-carried in registers: support() is inlined, there is no call to keep registers free for)
   {
     V3d v0 = ld3(o.gpos + 3 * g1) - ld3(o.gpos + 3 * g2);
     if (fabs(v0.x) < eps && fabs(v0.y) < eps && fabs(v0.z) < eps) v0.x += eps * 10;
@@ -204,32 +205,26 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       d = normalized(-v0);
     }
     __syncwarp();
-    if (lane == 0) { st3(P, v0); st3(P + 3, ld3(o.gpos + 3 * g1)); st3(P + 6, ld3(o.gpos + 3 * g2)); st3(P + 45, d); }
+    if (lane == 0) { st3(P, v0); st3(P + 3, ld3(o.gpos + 3 * g1)); st3(P + 6, ld3(o.gpos + 3 * g2)); }
     __syncwarp();
+    dcur = d;
   }
   int guard = 0, it = 0;
   WPE_CK_DECL;
 // publish the next direction and go round again
-#define WPE_NEXT_DIR() { __syncwarp(); if (lane == 0) st3(P + 45, d); __syncwarp(); WPE_CK(21); continue; }
+#define WPE_NEXT_DIR() { dcur = d; WPE_CK(21); continue; }
 #pragma unroll 1
   while (true) {
-    // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along the direction in P[45..47].  Nothing
-    //      but a few integers stays in registers across the two calls: direction, v0 and the first support point go
-    //      through the warp's shared-memory scratch (the version that kept them live spilled ~1 KB per thread to local
-    //      memory, i.e. to L2 with this kernel's shared-memory carve-out, on the critical path of every iteration)
-    {
-      const V3d a1 = support(t, o, verts4, g1, gb0, ld3(P + 45));
-      if (lane == 0) st3(P + 39, a1);
-    }
-    {
-      const V3d a2 = support(t, o, verts4, g2, gb0, -ld3(P + 45));
-      __syncwarp();
-      if (lane == 0) { st3(P + 42, a2); st3(P + 36, ld3(P + 39) - a2); }
-      __syncwarp();
-    }
+    // ---- the support evaluation: portal vertex 4 <- support of (g1 - g2) along the current direction.  support() is inlined:
+    //      the direction and the two support points stay in registers (through shared memory and two warp barriers per
+    //      iteration when support() was a call: +2 % with them in registers)
+    const V3d a1 = support(t, o, verts4, g1, gb0, dcur);
+    const V3d a2 = support(t, o, verts4, g2, gb0, -dcur);
+    const V3d v4 = a1 - a2;
+    __syncwarp();   // every lane is done with the previous contents of portal vertex 4
+    if (lane == 0) { st3(P + 36, v4); st3(P + 39, a1); st3(P + 42, a2); }   // read by others only through pcopy (which synchronises first)
     WPE_CK(20);
-    const V3d v4 = ld3(P + 36);
-    V3d d = ld3(P + 45);
+    V3d d = dcur;
     const V3d v0 = ld3(P);
     double dt = dot(v4, d);
     bool enter_refine = false;
@@ -255,7 +250,7 @@ __device__ __noinline__ bool mpr(const Tab& t, const Slice& o, Slice& s, const f
       if (is_zero(dot(d, d))) {
         if (fabs(v4.x) < eps && fabs(v4.y) < eps && fabs(v4.z) < eps) return false;
         const double dep = norm(v4);
-        const V3d dir = v4 * (1.0 / dep), pos = (ld3(P + 39) + ld3(P + 42)) * 0.5;
+        const V3d dir = v4 * (1.0 / dep), pos = (a1 + a2) * 0.5;
         if (lane == 0) {
           out7[0] = dep; out7[1] = dir.x; out7[2] = dir.y; out7[3] = dir.z; out7[4] = pos.x; out7[5] = pos.y; out7[6] = pos.z;
           if (sep) sep[3] = 2.f;
