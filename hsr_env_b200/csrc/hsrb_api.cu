@@ -110,6 +110,14 @@ cudaError_t launch(int G, const KArgs& a, int grid, size_t smem, cudaStream_t s)
     default: return hsrb_launch_step_32(a, grid, smem, s);
   }
 }
+cudaError_t launch_aux(int G, const KArgs& a, int grid, size_t smem, cudaStream_t s) {
+  switch (G) {
+    case 4: return hsrb_launch_aux_4(a, grid, smem, s);
+    case 8: return hsrb_launch_aux_8(a, grid, smem, s);
+    case 16: return hsrb_launch_aux_16(a, grid, smem, s);
+    default: return hsrb_launch_aux_32(a, grid, smem, s);
+  }
+}
 
 // Choose lanes-per-environment and the grid: as many lanes per env as keeps every environment resident in
 // one wave (more lanes = shorter dependent chain per substep), otherwise fewer lanes / a grid-stride loop.
@@ -336,7 +344,8 @@ int run(hsrb* h, KArgs& a, void* stream) {
   a.ws_bytes = h->ws_bytes;
   a.m.ncon_max = h->dm.ncon_max; a.m.nefc_max = h->dm.nefc_max;
   size_t smem = (size_t)h->ws_bytes * (32 / h->lanes);
-  CU(launch(h->lanes, a, h->grid, smem, (cudaStream_t)stream));
+  if (a.mode == MODE_RESET || a.mode == MODE_FORWARD) CU(launch_aux(h->lanes, a, h->grid, smem, (cudaStream_t)stream));   // the lean instance
+  else CU(launch(h->lanes, a, h->grid, smem, (cudaStream_t)stream));
   h->launches++;
   return 0;
 }

@@ -61,7 +61,10 @@ __device__ __forceinline__ void store_state(const KArgs& a, WS<float>& w, const 
 }
 
 // The action kernel.  blockDim.x = 32 (one warp), 32/G environments per block, grid-stride over environments.
-template <int G>
+// FULL = false: the same kernel without the STEP / DEBUG modes (reset and forward launches): a few KB of code instead of
+// several hundred, which matters when it runs between two action kernels on a cold L2 (bench.py flushes L2 between timed
+// steps: the masked reset through the full kernel's binary cost 1.4-2.6 ms of instruction fetch from DRAM, 0.03 ms warm).
+template <int G, bool FULL = true>
 __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ KArgs a) {
   HSRB_DYN_SMEM(smem);
   DevGrp<G> g;
@@ -76,9 +79,9 @@ __global__ void __launch_bounds__(32) hsrb_step_kernel(const __grid_constant__ K
     g.sync();
     bool success = false;
     int taken = 0;
-    if (a.mode == MODE_STEP) {
+    if (FULL && a.mode == MODE_STEP) {
       taken = env_action(a.m, a.cfg, w, g, a.nsub, success);
-    } else if (a.mode == MODE_DEBUG) {
+    } else if (FULL && a.mode == MODE_DEBUG) {
       forward(a.m, w, g);
       euler_solve(a.m, w, g);
       if (g.lane == 0) euler_lane0(a.m, w);
@@ -347,16 +350,22 @@ cudaError_t hsrb_launch_step_lock(const KArgs& a, int grid, int threads, size_t 
 // per-G entry points, one translation unit each (parallel compilation)
 #define HSRB_DECL_G(G)                                                \
   cudaError_t hsrb_prepare_step_##G(size_t smem, int* blocks_per_sm); \
-  cudaError_t hsrb_launch_step_##G(const KArgs& a, int grid, size_t smem, cudaStream_t s);
+  cudaError_t hsrb_launch_step_##G(const KArgs& a, int grid, size_t smem, cudaStream_t s); \
+  cudaError_t hsrb_launch_aux_##G(const KArgs& a, int grid, size_t smem, cudaStream_t s);
 HSRB_DECL_G(4) HSRB_DECL_G(8) HSRB_DECL_G(16) HSRB_DECL_G(32)
 
 #define HSRB_DEFINE_G(G)                                                                                               \
   cudaError_t hsrb_prepare_step_##G(size_t smem, int* bps) {                                                           \
     cudaError_t e = cudaFuncSetAttribute(hsrb_step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); /* per function, shared by all handles */ \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hsrb_step_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
     if (e != cudaSuccess) return e;                                                                                    \
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, hsrb_step_kernel<G>, 32, smem);                          \
   }                                                                                                                    \
   cudaError_t hsrb_launch_step_##G(const KArgs& a, int grid, size_t smem, cudaStream_t s) {                            \
     hsrb_step_kernel<G><<<grid, 32, smem, s>>>(a);                                                                     \
+    return cudaGetLastError();                                                                                         \
+  }                                                                                                                    \
+  cudaError_t hsrb_launch_aux_##G(const KArgs& a, int grid, size_t smem, cudaStream_t s) { /* reset / forward launches */ \
+    hsrb_step_kernel<G, false><<<grid, 32, smem, s>>>(a);                                                              \
     return cudaGetLastError();                                                                                         \
   }
